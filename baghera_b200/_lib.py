@@ -1,0 +1,115 @@
+"""ctypes binding of libbaghera_b200.so (C ABI: include/baghera_b200.h).
+
+The library is built in-tree by ``baghera_b200/csrc/Makefile`` (``__graft_entry__.build()``).
+Loading fails loudly when it is missing: there is no eager / CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbaghera_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+BGH_ABI_VERSION = 1
+BGH_OK, BGH_EINVAL, BGH_ECUDA, BGH_ENOMEM, BGH_ESTATE, BGH_ENODEV = 0, -1, -2, -3, -4, -5
+BGH_MODEL_GENE_NORMAL, BGH_MODEL_GW_NORMAL = 0, 1
+
+
+class BghError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("baghera_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class bgh_cfg(ctypes.Structure):
+    _fields_ = [
+        ("abi_version", ctypes.c_int32),
+        ("device", ctypes.c_int32),
+        ("model", ctypes.c_int32),
+        ("fix_intercept", ctypes.c_int32),
+        ("n_snps", ctypes.c_int64),
+        ("n_genes", ctypes.c_int32),
+        ("n_chains", ctypes.c_int32),
+        ("c", ctypes.c_double),
+        ("n_genes_total", ctypes.c_int32),
+        ("first_gene_partial", ctypes.c_int32),
+        ("last_gene_partial", ctypes.c_int32),
+        ("first_gene_row", ctypes.c_int32),
+        ("last_gene_row", ctypes.c_int32),
+        ("n_shared_rows", ctypes.c_int32),
+        ("sm_count_override", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 5),
+    ]
+
+
+_vp = ctypes.c_void_p
+_i32, _i64, _dbl = ctypes.c_int32, ctypes.c_int64, ctypes.c_double
+_pi32 = ctypes.POINTER(ctypes.c_int32)
+_pi64 = ctypes.POINTER(ctypes.c_int64)
+_pdbl = ctypes.POINTER(ctypes.c_double)
+
+# name -> (restype, argtypes); mirrors include/baghera_b200.h one to one
+SIGNATURES = {
+    "bgh_cfg_default": (None, [ctypes.POINTER(bgh_cfg)]),
+    "bgh_version": (ctypes.c_char_p, []),
+    "bgh_create": (_i32, [ctypes.POINTER(_vp), ctypes.POINTER(bgh_cfg)]),
+    "bgh_destroy": (None, [_vp]),
+    "bgh_last_error": (ctypes.c_char_p, [_vp]),
+    "bgh_dim": (_i32, [_vp]),
+    "bgh_chain_stride": (_i32, [_vp]),
+    "bgh_payload_rows": (_i32, [_vp]),
+    "bgh_upload": (_i32, [_vp, _vp, _vp, _vp]),
+    "bgh_lik_const": (_dbl, [_vp]),
+    "bgh_logp_grad": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "bgh_logp_grad_local": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "bgh_logp_grad_finish": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "bgh_logp_grad_host": (_i32, [_vp, _vp, _vp, _vp]),
+    "bgh_logp_grad_host_stream": (_i32, [_vp, _i32, _vp, _vp, _vp]),
+    "bgh_to_device_layout": (_i32, [_vp, _vp, _vp, _vp]),
+    "bgh_from_device_layout": (_i32, [_vp, _vp, _vp, _vp]),
+    "bgh_n_groups": (_i32, [_vp]),
+    "bgh_get_partition": (_i32, [_vp, _pi32, _i32]),
+    "bgh_n_split_genes": (_i32, [_vp]),
+    "bgh_launch_count": (_i64, [_vp]),
+    "bgh_set_profiling": (_i32, [_vp, _i32]),
+    "bgh_kernel_time_ms": (_i32, [_vp, _pdbl, _pdbl, _pi64, _i32]),
+    "bgh_dfma_peak": (_i32, [_vp, _pdbl]),
+    "bgh_debug_plan": (_i32, [_i64, _pi32, _i32, _i32, _i32, _i32, _pi32, _pi32, _pi32, _pi32, _pi32, _pi32, _i32]),
+}
+
+_LIB = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("building libbaghera_b200.so failed:\n" + out.stdout + out.stderr)
+    if verbose:
+        print(out.stdout)
+    return LIB_PATH
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "libbaghera_b200.so is missing (%s). Build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` or `make -C baghera_b200/csrc`. There is no CPU fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)          # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def check(rc: int, ctx=None):
+    if rc != BGH_OK:
+        msg = lib().bgh_last_error(ctx)
+        raise BghError(rc, msg.decode() if msg else "?")

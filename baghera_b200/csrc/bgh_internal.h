@@ -1,0 +1,98 @@
+// Internal declarations shared by the translation units of libbaghera_b200.so.
+// Not part of the public ABI (see include/baghera_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "baghera_b200.h"
+
+namespace bgh {
+
+constexpr int kLikThreads = 512;               // one CTA per SM, 16 warps
+constexpr int kLikWarps = kLikThreads / 32;
+constexpr int kChunk = 128;                    // SNPs staged per warp per chunk
+constexpr int kFinThreads = 1024;
+constexpr int kShortSplit = 32;                // split lists up to this length are summed by one warp
+constexpr double kLog2Pi = 1.8378770664093454835606594728112;
+
+enum : int { kHeadPartial = 1, kTailPartial = 2 };
+
+// Work decomposition of the gene-sorted SNP array (host side, no CUDA needed).
+// A "group" is CL consecutive lanes of a warp that walk one contiguous SNP range
+// sequentially; gene boundaries are therefore group-uniform and per-gene sums are plain
+// sequential fp64 accumulations (deterministic, no atomics).
+struct Plan {
+    int n_groups = 0;
+    std::vector<int32_t> off;          // [n_groups+1] range offsets
+    std::vector<int32_t> flags;        // [n_groups]   kHeadPartial | kTailPartial
+    // genes whose sum is assembled from slot partials: CSR over slot indices.
+    // slot index s < n_groups  : head slot of group s
+    // slot index s >= n_groups : tail slot of group s - n_groups
+    int n_long = 0;                    // split genes with > kShortSplit slots come first
+    std::vector<int32_t> split_gene;   // [ns]
+    std::vector<int32_t> split_row;    // [ns] payload row (>=0) if the gene is rank-shared, else -1
+    std::vector<int32_t> split_ptr;    // [ns+1]
+    std::vector<int32_t> split_slots;  // [split_ptr[ns]]
+};
+
+// gid must be sorted ascending.  Returns 0 or BGH_EINVAL (message in err).
+int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_groups, bool first_partial,
+               bool last_partial, int first_row, int last_row, Plan* plan, std::string* err);
+
+struct LikParams {
+    const float* chi2;
+    const float* ld;
+    const int* gid;
+    const int4* groups;   // {a, b, flags, 0}
+    const double* q;      // [D][Cp]
+    double* grad;         // [D][Cp]
+    double* slots;        // [2*NG][Cp]
+    double* part;         // [nCTA][4][Cp]
+    int Cp;
+    int G;
+    int NG;
+    int model;
+    int fix;
+    double c;
+};
+
+struct FinParams {
+    const double* q;
+    double* grad;
+    double* logp;
+    const double* slots;
+    const double* part;
+    double* payload;      // [(4+n_shared)][Cp]
+    const int* split_gene;
+    const int* split_row;
+    const int* split_ptr;
+    const int* split_slots;
+    int n_split;
+    int n_long;           // split genes [0, n_long) have > kShortSplit slots (one CTA each)
+    int n_cta;            // CTAs of the likelihood kernel (rows of part)
+    int Cp;
+    int G_total;
+    int model;
+    int fix;
+    int finish_inline;    // 1: single rank, write logp / grad rows 0..2 here
+    double c;
+    double lik_const;
+    // finish-only
+    int first_gene_row, last_gene_row, G_local;
+};
+
+// kernel launchers (bgh_lik.cu)
+cudaError_t launch_lik(const LikParams& p, int CL, int CPL, int n_cta, int chain_blocks, cudaStream_t s);
+cudaError_t launch_finalize(const FinParams& p, cudaStream_t s);
+cudaError_t launch_finish(const FinParams& p, cudaStream_t s);
+cudaError_t launch_transpose_in(const double* q_cd, double* q_dc, int C, int Cp, int D, cudaStream_t s);
+cudaError_t launch_transpose_out(const double* x_dc, double* x_cd, int C, int Cp, int D, cudaStream_t s);
+cudaError_t launch_dfma_probe(double* out, int iters, int n_cta, cudaStream_t s);
+cudaError_t lik_configure();   // opt-in dynamic shared memory, once per process
+size_t lik_smem_bytes();
+
+}  // namespace bgh

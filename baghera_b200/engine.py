@@ -1,0 +1,186 @@
+"""Device engine: owns one ``bgh_ctx`` (one GPU / rank) and exposes logp+grad on torch tensors.
+
+PyTorch is plumbing here (device memory, streams, torch.distributed); all arithmetic of the path
+runs in libbaghera_b200.so.  Replaces ``model.logp_dlogp_function()`` of the PyMC3 model built at
+ref: baghera_tool/gene_regression.py:77-98 / baghera_tool/heritability.py:44-55.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import BGH_MODEL_GENE_NORMAL, BGH_MODEL_GW_NORMAL, BghError, bgh_cfg, check
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class Engine:
+    """One context per GPU.  Parameters live on the device as float64[D, Cp] (gene-major, chain-minor)."""
+
+    def __init__(self, chi2, ld, gene_id, n_genes, c, n_chains, model="gene", fix_intercept=False,
+                 device=0, shard=None):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("baghera_b200.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.torch = torch
+        self.L = _lib.lib()
+        chi2 = np.ascontiguousarray(chi2, dtype=np.float32)
+        ld = np.ascontiguousarray(ld, dtype=np.float32)
+        cfg = bgh_cfg()
+        self.L.bgh_cfg_default(ctypes.byref(cfg))
+        cfg.device = int(device)
+        cfg.model = BGH_MODEL_GENE_NORMAL if model == "gene" else BGH_MODEL_GW_NORMAL
+        cfg.fix_intercept = int(bool(fix_intercept))
+        cfg.n_snps = int(chi2.shape[0])
+        cfg.n_genes = int(n_genes) if model == "gene" else 1
+        cfg.n_chains = int(n_chains)
+        cfg.c = float(c)
+        if shard is not None:
+            for k, v in shard.items():
+                setattr(cfg, k, int(v))
+        self.cfg = cfg
+        self.model = model
+        self.device = torch.device("cuda", int(device))
+        ctx = ctypes.c_void_p()
+        check(self.L.bgh_create(ctypes.byref(ctx), ctypes.byref(cfg)))
+        self.ctx = ctx
+        gid = None
+        if model == "gene":
+            gid = np.ascontiguousarray(gene_id, dtype=np.int32)
+            if gid.shape[0] != chi2.shape[0]:
+                raise ValueError("gene_id length mismatch")
+        check(self.L.bgh_upload(ctx, chi2.ctypes.data_as(ctypes.c_void_p), ld.ctypes.data_as(ctypes.c_void_p),
+                                gid.ctypes.data_as(ctypes.c_void_p) if gid is not None else None), ctx)
+        self.M = int(chi2.shape[0])
+        self.C = int(n_chains)
+        self.D = int(self.L.bgh_dim(ctx))
+        self.Cp = int(self.L.bgh_chain_stride(ctx))
+        self.payload_rows = int(self.L.bgh_payload_rows(ctx))
+        self.lik_const = float(self.L.bgh_lik_const(ctx))
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.L.bgh_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def empty_params(self):
+        return self.torch.empty((self.D, self.Cp), dtype=self.torch.float64, device=self.device)
+
+    def to_device_layout(self, q_cd):
+        """float64[C, D] (host numpy or device tensor, PyMC3 chain-major) -> device float64[D, Cp]."""
+        t = self.torch
+        q = t.as_tensor(np.asarray(q_cd, dtype=np.float64) if not t.is_tensor(q_cd) else q_cd).to(
+            self.device, t.float64).contiguous()
+        assert q.shape == (self.C, self.D), (q.shape, (self.C, self.D))
+        out = self.empty_params()
+        check(self.L.bgh_to_device_layout(self.ctx, _ptr(q), _ptr(out), self._stream()), self.ctx)
+        return out
+
+    def from_device_layout(self, x_dc):
+        t = self.torch
+        out = t.empty((self.C, self.D), dtype=t.float64, device=self.device)
+        check(self.L.bgh_from_device_layout(self.ctx, _ptr(x_dc), _ptr(out), self._stream()), self.ctx)
+        return out
+
+    # ------------------------------------------------------------------ the hot path
+    def logp_grad(self, q_dc, logp=None, grad=None):
+        """Async on the current torch stream. q_dc: float64[D, Cp] -> (logp[Cp], grad[D, Cp])."""
+        t = self.torch
+        if logp is None:
+            logp = t.empty(self.Cp, dtype=t.float64, device=self.device)
+        if grad is None:
+            grad = t.empty_like(q_dc)
+        check(self.L.bgh_logp_grad(self.ctx, _ptr(q_dc), _ptr(logp), _ptr(grad), self._stream()), self.ctx)
+        return logp, grad
+
+    def logp_grad_local(self, q_dc, grad, payload):
+        check(self.L.bgh_logp_grad_local(self.ctx, _ptr(q_dc), _ptr(grad), _ptr(payload), self._stream()), self.ctx)
+
+    def logp_grad_finish(self, q_dc, payload, logp, grad):
+        check(self.L.bgh_logp_grad_finish(self.ctx, _ptr(q_dc), _ptr(payload), _ptr(logp), _ptr(grad),
+                                          self._stream()), self.ctx)
+
+    def logp_grad_host(self, q_cd, logp=None, grad=None, n_evals=None):
+        """B1' with host buffers: q float64[C, D] (or [n, C, D]) numpy -> (logp, grad) numpy."""
+        q = np.ascontiguousarray(q_cd, dtype=np.float64)
+        batched = q.ndim == 3
+        n = q.shape[0] if batched else 1
+        assert q.shape[-2:] == (self.C, self.D)
+        if logp is None:
+            logp = np.empty((n, self.C) if batched else (self.C,))
+        if grad is None:
+            grad = np.empty_like(q)
+        check(self.L.bgh_logp_grad_host_stream(self.ctx, n, q.ctypes.data_as(ctypes.c_void_p),
+                                               logp.ctypes.data_as(ctypes.c_void_p),
+                                               grad.ctypes.data_as(ctypes.c_void_p)), self.ctx)
+        return logp, grad
+
+    def logp_grad_host_ptr(self, n, q_ptr, logp_ptr, grad_ptr):
+        check(self.L.bgh_logp_grad_host_stream(self.ctx, int(n), ctypes.c_void_p(q_ptr), ctypes.c_void_p(logp_ptr),
+                                               ctypes.c_void_p(grad_ptr)), self.ctx)
+
+    # ------------------------------------------------------------------ introspection
+    def partition(self):
+        n = int(self.L.bgh_n_groups(self.ctx)) + 1
+        off = np.empty(n, dtype=np.int32)
+        check(self.L.bgh_get_partition(self.ctx, off.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), n), self.ctx)
+        return off
+
+    @property
+    def n_split_genes(self):
+        return int(self.L.bgh_n_split_genes(self.ctx))
+
+    @property
+    def launch_count(self):
+        return int(self.L.bgh_launch_count(self.ctx))
+
+    def set_profiling(self, on=True):
+        check(self.L.bgh_set_profiling(self.ctx, int(bool(on))), self.ctx)
+
+    def kernel_time_ms(self, reset=True):
+        a, b, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+        check(self.L.bgh_kernel_time_ms(self.ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(n), int(reset)), self.ctx)
+        return a.value, b.value, n.value
+
+    def dfma_peak(self):
+        v = ctypes.c_double()
+        check(self.L.bgh_dfma_peak(self.ctx, ctypes.byref(v)), self.ctx)
+        return v.value
+
+
+def debug_plan(gid_sorted, G, n_groups, first_partial=False, last_partial=False):
+    """Host-only work plan (no GPU): returns dict(off, flags, split_gene, split_ptr, split_slots)."""
+    L = _lib.lib()
+    gid = np.ascontiguousarray(gid_sorted, dtype=np.int32)
+    M = gid.shape[0]
+    cap = 2 * n_groups + 8
+    off = np.zeros(n_groups + 1, np.int32)
+    flags = np.zeros(n_groups, np.int32)
+    ns = ctypes.c_int32()
+    sg = np.zeros(cap, np.int32)
+    sp = np.zeros(cap + 1, np.int32)
+    ss = np.zeros(cap, np.int32)
+    P = ctypes.POINTER(ctypes.c_int32)
+    rc = L.bgh_debug_plan(M, gid.ctypes.data_as(P), int(G), int(n_groups), int(first_partial), int(last_partial),
+                          off.ctypes.data_as(P), flags.ctypes.data_as(P), ctypes.byref(ns), sg.ctypes.data_as(P),
+                          sp.ctypes.data_as(P), ss.ctypes.data_as(P), cap)
+    check(rc)
+    n = ns.value
+    return dict(off=off, flags=flags, split_gene=sg[:n].copy(), split_ptr=sp[:n + 1].copy(),
+                split_slots=ss[:sp[n]].copy())

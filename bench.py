@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the BAGHERA hot path on B200 (contract: see DESIGN.md §Measurement).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # CPU restatement of the reference path
+
+Metric: single-chain full-dataset logp+grad evaluations per second ("chain-evals/s") on the
+UKBB-shaped synthetic workload BASELINE.json quotes: 1.1M SNPs x 15k genes x 64 chains (cfg3).
+A step = one batched evaluation (all 64 chains, all SNPs) = 64 chain-evals.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "logp_grad_chain_evals_per_sec"
+UNIT = "chain-evals/s"
+WORKLOADS = {
+    "cfg3": dict(M=1_100_000, G=15_000, C=64, desc="UKBB-shaped synthetic 1.1M SNPs x 15k genes, 64 chains, normal model"),
+    "cfg2": dict(M=1_100_000, G=15_000, C=4, desc="UKBB-shaped synthetic 1.1M SNPs x 15k genes, 4 chains, normal model"),
+    "cfg1": dict(M=20_000, G=200, C=4, desc="synthetic 20k SNPs x 200 genes, 4 chains, normal model"),
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index=0, period=0.02):
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+            return self
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=1.0)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def shard_dataset(d, rank, world):
+    """Gene-block sharding of the gene-sorted SNP array: contiguous, balanced by SNP count.
+
+    Returns (chi2, ld, local_gene_id, n_local_genes, shard_cfg, gene_lo).  A gene cut by a rank
+    boundary is replicated on the ranks it touches; its residual sum travels in the all-reduce payload.
+    """
+    order = np.argsort(d.gene_id, kind="stable")
+    gid = d.gene_id[order]
+    M = gid.shape[0]
+    cuts = [int(round(k * M / world)) for k in range(world + 1)]
+    shared = []                                   # genes cut by a rank boundary, in order
+    for k in range(1, world):
+        x = cuts[k]
+        if 0 < x < M and gid[x - 1] == gid[x]:
+            g = int(gid[x])
+            if not shared or shared[-1] != g:
+                shared.append(g)
+    a, b = cuts[rank], cuts[rank + 1]
+    g_lo, g_hi = int(gid[a]), int(gid[b - 1])
+    first_partial = a > 0 and gid[a - 1] == gid[a]
+    last_partial = b < M and gid[b] == gid[b - 1]
+    cfg = dict(n_genes_total=d.G, n_shared_rows=len(shared),
+               first_gene_partial=int(first_partial), last_gene_partial=int(last_partial),
+               first_gene_row=shared.index(g_lo) if (first_partial or (g_lo in shared)) and g_lo in shared else -1,
+               last_gene_row=shared.index(g_hi) if g_hi in shared else -1)
+    sel = order[a:b]
+    return d.chi2[sel], d.ld[sel], (gid[a:b] - g_lo).astype(np.int32), g_hi - g_lo + 1, cfg, g_lo
+
+
+def run_cpu_baseline(d, C, target_seconds=10.0, n_threads=0):
+    """Times the C restatement of the reference CPU path (oracle/oracle_c.c) on the host cores."""
+    from oracle.c_oracle import COracle, num_threads
+    from baghera_b200 import synth
+    T = n_threads or num_threads()
+    co = COracle(d.chi2, d.ld, d.gene_id, d.G, d.c)
+    Q = synth.jittered_start(d.G + 3, max(T, 1), seed=3)
+    t0 = time.perf_counter()
+    co.logp_grad_batch(Q, n_threads=T)
+    t1 = time.perf_counter() - t0
+    reps = int(max(1, min(200, target_seconds / max(t1, 1e-4))))
+    Qb = np.tile(Q, (reps, 1))
+    t0 = time.perf_counter()
+    co.logp_grad_batch(Qb, n_threads=T)
+    dt = time.perf_counter() - t0
+    n = Qb.shape[0]
+    return {"value": n / dt, "unit": UNIT, "cores": T, "kind": "port",
+            "sample": "%d chain-evals of the full %dx%d dataset (one chain per thread, %d threads, %.1f s); "
+                      "C restatement of the Theano op sequence, not PyMC3 itself" % (n, d.M, d.G, T, dt),
+            "ms_per_chain_eval_per_core": dt / n * T * 1e3}
+
+
+def bench_reference(args, wl):
+    """Reference arm: the reference's own CPU implementation of the path.  PyMC3 3.6/theano cannot be
+    installed here, so this times oracle/oracle_c.c (kind 'port') with every host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from baghera_b200 import synth
+    d = synth.make_arrays(wl["M"], wl["G"])
+    from oracle.c_oracle import COracle, num_threads
+    T = num_threads()
+    co = COracle(d.chi2, d.ld, d.gene_id, d.G, d.c)
+    # a step = T chain-evals (one per host thread): a bounded sample of the 64-chain batched evaluation
+    Q = synth.jittered_start(d.G + 3, T, seed=3)
+    for _ in range(args.warmup):
+        co.logp_grad_batch(Q, n_threads=T)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        co.logp_grad_batch(Q, n_threads=T)
+    dt = time.perf_counter() - t0
+    value = args.steps * T / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": wl["desc"], "sample": "%d chain-evals per step (one per host thread)" % T},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": T, "kind": "port",
+                         "sample": "%d steps x %d chain-evals, full dataset per eval; C restatement of the "
+                                   "reference's Theano op sequence (PyMC3 not installable)" % (args.steps, T)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def bench_gpu(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    from baghera_b200 import synth
+    from baghera_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    M, G, C = wl["M"], wl["G"], wl["C"]
+    d = synth.make_arrays(M, G)
+    D = G + 3
+    Q = synth.jittered_start(D, C, seed=1)
+
+    if world == 1:
+        eng = Engine(d.chi2, d.ld, d.gene_id, G, d.c, C, device=local_rank)
+        q_dev = eng.to_device_layout(Q)
+        g_lo = 0
+    else:
+        chi2, ld, gid, G_loc, scfg, g_lo = shard_dataset(d, rank, world)
+        eng = Engine(chi2, ld, gid, G_loc, d.c, C, device=local_rank, shard=scfg)
+        Qloc = np.concatenate([Q[:, :3], Q[:, 3 + g_lo: 3 + g_lo + G_loc]], axis=1)
+        q_dev = eng.to_device_layout(Qloc)
+    Cp = eng.Cp
+    logp = torch.empty(Cp, dtype=torch.float64, device=dev)
+    grad = torch.zeros_like(q_dev)
+    payload = torch.zeros((eng.payload_rows, Cp), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step():
+        if world == 1:
+            eng.logp_grad(q_dev, logp, grad)
+        else:
+            eng.logp_grad_local(q_dev, grad, payload)
+            dist.all_reduce(payload)
+            eng.logp_grad_finish(q_dev, payload, logp, grad)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, L2 flushed between steps, per-step CUDA events ---------------
+    K = args.steps
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    eng.set_profiling(True)
+    launches0 = eng.launch_count
+    clocks = ClockSampler(local_rank).start() if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    prof_lik, prof_fin, prof_n = 0.0, 0.0, 0
+    for i in range(K):
+        if not args.no_flush:
+            flush.fill_(i & 0xFF)
+        ev0[i].record()
+        step()
+        ev1[i].record()
+        if (i + 1) % 2000 == 0:                    # drain the library's event ring
+            a, b, n = eng.kernel_time_ms(reset=True)
+            prof_lik += a * n; prof_fin += b * n; prof_n += n
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - wall0
+    a, b, n = eng.kernel_time_ms(reset=True)
+    prof_lik += a * n; prof_fin += b * n; prof_n += n
+    eng.set_profiling(False)
+    clk = clocks.stop() if clocks else None
+    launches = eng.launch_count - launches0
+    step_ms = sum(e0.elapsed_time(e1) for e0, e1 in zip(ev0, ev1)) / K
+    t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms = float(t.item())
+    value = C / (step_ms * 1e-3)
+
+    # ---- steady state (no flush, back-to-back: the sampler's regime, SNP stream L2 resident) -----
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_ss = min(max(K, 50), 2000)
+    e0.record()
+    for _ in range(n_ss):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ss_ms = e0.elapsed_time(e1) / n_ss
+
+    line = None
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        lik_ms = prof_lik / max(prof_n, 1)
+        fin_ms = prof_fin / max(prof_n, 1)
+        Ml, Dl = eng.M, eng.D
+        b_alg = 12.0 * Ml + 16.0 * C * Dl + 8.0 * C           # SNP stream + read q + write grad + logp
+        achieved = b_alg / (lik_ms * 1e-3) / 1e9 if lik_ms > 0 else 0.0
+        dp_instr = 6.0 * Ml * C
+        try:
+            dfma_peak = eng.dfma_peak()
+        except Exception:
+            dfma_peak = None
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+                    "kernel": "lik_kernel", "kernel_ms": lik_ms, "finalize_ms": fin_ms,
+                    "algorithmic_bytes_per_launch": b_alg,
+                    "note": "at C=64 the kernel is FP64-pipe bound (6 DP instr per SNP x chain), see fp64_roofline"}
+        fp64 = {"achieved_ginstr_s": dp_instr / (lik_ms * 1e-3) / 1e9 if lik_ms > 0 else 0.0,
+                "peak_ginstr_s": dfma_peak, "unit": "G FP64 lane-instr/s",
+                "frac": (dp_instr / (lik_ms * 1e-3) / 1e9 / dfma_peak) if (dfma_peak and lik_ms > 0) else None,
+                "peak_source": "bgh_dfma_peak microbenchmark, same process", "dp_instr_per_launch": dp_instr}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "M": M, "G": G, "chains": C,
+                       "parallelism": "single GPU" if world == 1 else "gene-block SNP sharding x%d + NCCL all-reduce of %d x %d fp64 payload" % (world, eng.payload_rows, Cp),
+                       "l2": "not flushed" if args.no_flush else "flushed between steps (256 MiB write, outside the per-step events)",
+                       "timing": "per-step CUDA events on the launch stream, max over ranks"},
+            "batched_evals_per_sec": 1e3 / step_ms,
+            "steady_state": {"ms_per_step": ss_ms, "value": C / (ss_ms * 1e-3), "note": "no L2 flush, back-to-back launches (sampler regime)"},
+            "roofline": roofline, "fp64_roofline": fp64,
+            "gpu_launches": int(launches), "clocks": clk, "wall_s_timed_region": wall,
+        }
+    # ---- e2e: host buffers through the C ABI (H2D + transposes + kernels + D2H every step) --------
+    if world == 1:
+        n_e2e = int(min(max(K // 10, 8), 64))
+        qh = torch.empty((n_e2e, C, D), dtype=torch.float64).pin_memory()
+        gh = torch.empty((n_e2e, C, D), dtype=torch.float64).pin_memory()
+        lh = torch.empty((n_e2e, C), dtype=torch.float64).pin_memory()
+        qh.copy_(torch.from_numpy(np.broadcast_to(Q, (n_e2e, C, D)).copy()))
+        eng.logp_grad_host_ptr(2, qh.data_ptr(), lh.data_ptr(), gh.data_ptr())   # warm-up (allocs staging)
+        l0 = eng.launch_count
+        t0 = time.perf_counter()
+        eng.logp_grad_host_ptr(n_e2e, qh.data_ptr(), lh.data_ptr(), gh.data_ptr())
+        dt = time.perf_counter() - t0
+        line["e2e"] = {"value": n_e2e * C / dt, "unit": UNIT, "h2d_bytes_per_step": C * D * 8,
+                       "d2h_bytes_per_step": C * D * 8 + C * 8, "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3,
+                       "api": "bgh_logp_grad_host_stream (pinned host q[C][D] -> logp[C], grad[C][D]; copies, layout "
+                              "transposes and kernels of consecutive steps overlapped on 3 streams)",
+                       "gpu_launches": eng.launch_count - l0}
+        # check the e2e result against the device path
+        lp_dev = logp[:C].cpu().numpy()
+        assert np.allclose(lh[-1].numpy(), lp_dev, rtol=1e-12), "e2e result differs from device path"
+    elif rank == 0:
+        line["e2e"] = None
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = run_cpu_baseline(d, C, target_seconds=args.cpu_seconds)
+    if rank == 0:
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        if args.steps > 50:
+            args.steps = 50          # each step is ~1 s of CPU work at full size; keep the run bounded
+        bench_reference(args, wl)
+    else:
+        bench_gpu(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,157 @@
+/*
+ * baghera_b200.h — C ABI of the B200-native BAGHERA hot path.
+ *
+ * The reference (stracquadaniolab/baghera v2.2.0) has no FFI: the path sits behind a Python
+ * operator boundary and, inside PyMC3, a numerical callback.  Each entry point below cites
+ * the reference interface it replaces (paths are relative to the reference checkout):
+ *
+ *   B1  analyse_normal(snps_object, ..., SWEEPS, TUNE, CHAINS, CORES, N_1kG, fix_intercept)
+ *       baghera_tool/gene_regression.py:30-40   (model build :77-98, pm.sample :100-106)
+ *   B1' model.logp_dlogp_function()(q[D]) -> (logp, grad[D])     [PyMC3 3.6, pymc3/model.py]
+ *       parameter order = variable creation order, gene_regression.py:78-81:
+ *           q = [W_log__, e, mi_logodds__, beta_0 .. beta_{G-1}]         D = G + 3
+ *       genome-wide model, baghera_tool/heritability.py:44-55:
+ *           q = [e, mi_logodds__]                                        D = 2
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative BGH_E* code; the message is available
+ *     from bgh_last_error(ctx) (bgh_last_error(NULL) for failures of bgh_create).  No C++
+ *     exception crosses this boundary.
+ *   - a context is bound to one CUDA device, owns the uploaded SNP arrays and all scratch, and is
+ *     NOT thread-safe: one context per GPU / rank.
+ *   - "device" pointers are plain CUDA device pointers owned by the caller (e.g. torch tensors'
+ *     data_ptr()); `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     Device entry points are asynchronous on that stream and never synchronise.
+ *   - device parameter layout is gene-major / chain-minor:  q[d * Cp + chain],  d in [0, D),
+ *     Cp = bgh_chain_stride(ctx) >= C (chains padded to the kernel's chain-group width; padded
+ *     chains must hold finite values, e.g. a copy of chain 0; their outputs are unspecified).
+ *   - host entry points use PyMC3's chain-major layout q[chain * D + d] and exclude padding.
+ */
+#ifndef BAGHERA_B200_H
+#define BAGHERA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BGH_ABI_VERSION 1
+
+enum {
+    BGH_OK = 0,
+    BGH_EINVAL = -1,   /* bad argument / inconsistent configuration       */
+    BGH_ECUDA = -2,    /* CUDA runtime error (message has the CUDA string) */
+    BGH_ENOMEM = -3,   /* host allocation failed                           */
+    BGH_ESTATE = -4,   /* call order violated (e.g. logp before upload)    */
+    BGH_ENODEV = -5    /* no usable sm_100 device                          */
+};
+
+enum {
+    BGH_MODEL_GENE_NORMAL = 0, /* gene_regression.py:77-98   */
+    BGH_MODEL_GW_NORMAL = 1    /* heritability.py:44-55      */
+};
+
+typedef struct bgh_ctx bgh_ctx;
+
+typedef struct bgh_cfg {
+    int32_t abi_version;   /* BGH_ABI_VERSION */
+    int32_t device;        /* CUDA device ordinal */
+    int32_t model;         /* BGH_MODEL_* */
+    int32_t fix_intercept; /* gene_regression.py:84-90 (e still sampled from its prior, Q8) */
+    int64_t n_snps;        /* M: SNPs in THIS context (this rank's shard) */
+    int32_t n_genes;       /* G: gene labels present in this shard, ids 0..G-1 (gw model: 1) */
+    int32_t n_chains;      /* C */
+    double  c;             /* n_patients / N_1kG  (gene_regression.py:95) */
+    /* --- gene-block sharding (single GPU: leave zero / -1 as set by bgh_cfg_default) --- */
+    int32_t n_genes_total;     /* G over all ranks; 0 => n_genes */
+    int32_t first_gene_partial;/* 1: this shard's first gene started on a previous rank */
+    int32_t last_gene_partial; /* 1: this shard's last gene continues on the next rank  */
+    int32_t first_gene_row;    /* payload row (>=0) of the first gene if it is rank-shared, else -1 */
+    int32_t last_gene_row;     /* payload row of the last gene if rank-shared, else -1 */
+    int32_t n_shared_rows;     /* rank-shared genes over all ranks (payload rows 4 .. 4+n-1) */
+    int32_t sm_count_override; /* 0 = query the device; tests may set it to build partitions on CPU */
+    int32_t reserved[5];
+} bgh_cfg;
+
+/* Fills *cfg with single-GPU defaults. */
+void bgh_cfg_default(bgh_cfg* cfg);
+
+/* Library / build identification ("baghera_b200 <abi> sm_100a ..."). */
+const char* bgh_version(void);
+
+/* Creates a context on cfg->device.  Fails with BGH_ENODEV when no CUDA device is usable:
+ * there is no CPU fallback.  Replaces the `with pm.Model()` block, gene_regression.py:77. */
+int bgh_create(bgh_ctx** out, const bgh_cfg* cfg);
+void bgh_destroy(bgh_ctx* ctx);
+const char* bgh_last_error(const bgh_ctx* ctx);
+
+/* Geometry the caller needs to size its tensors. */
+int32_t bgh_dim(const bgh_ctx* ctx);           /* D  (G+3 or 2) */
+int32_t bgh_chain_stride(const bgh_ctx* ctx);  /* Cp */
+int32_t bgh_payload_rows(const bgh_ctx* ctx);  /* 4 + n_shared_rows: rows of the all-reduce payload */
+
+/* Uploads the observed data in FILE order (host pointers): chi2 = stats = z^2 (snps.py:78),
+ * ld = transformed LD score >= 1 (snps.py:121), gene_id = rank of the SNP's gene label in sorted
+ * label order (gene_regression.py:61-71), unsorted (Q6).  The library stable-sorts by gene,
+ * builds the warp partition and precomputes sum_j -1/2 log(2 pi l_j).  gene_id may be NULL for
+ * the gw model.  Replaces the observed-variable construction gene_regression.py:93-98. */
+int bgh_upload(bgh_ctx* ctx, const float* chi2, const float* ld, const int32_t* gene_id);
+
+/* sum_j -1/2 log(2 pi l_j), the chain-independent constant of the likelihood (after upload). */
+double bgh_lik_const(const bgh_ctx* ctx);
+
+/* B1' on the device: q, grad are [D][Cp], logp is [Cp]; async on `stream`.
+ * Single-rank contexts only (n_shared_rows == 0). */
+int bgh_logp_grad(bgh_ctx* ctx, const double* q, double* logp, double* grad, void* stream);
+
+/* Sharded form: local pass writes this rank's gradient rows for its non-shared genes and the
+ * payload [bgh_payload_rows][Cp] = {sum r^2/l, sum r/l, sum(beta-mi), sum(beta-mi)^2, shared-gene
+ * sums ...}; the caller all-reduces (sum) the payload over ranks (NCCL) and calls _finish, which
+ * writes logp[Cp], grad rows 0..2 and the gradient rows of the rank-shared genes. */
+int bgh_logp_grad_local(bgh_ctx* ctx, const double* q, double* grad, double* payload, void* stream);
+int bgh_logp_grad_finish(bgh_ctx* ctx, const double* q, const double* payload, double* logp,
+                         double* grad, void* stream);
+
+/* B1' with HOST buffers in PyMC3's layout: q[C][D] -> logp[C], grad[C][D].  Copies H2D, transposes
+ * on the device, evaluates, transposes back and copies D2H; synchronous.  Buffers may be pageable
+ * or pinned (pinned is faster). */
+int bgh_logp_grad_host(bgh_ctx* ctx, const double* q, double* logp, double* grad);
+
+/* Pipelined host form used for throughput measurement: evaluates `n_evals` parameter batches
+ * q[n][C][D] -> logp[n][C], grad[n][C][D] with H2D / compute / D2H of consecutive batches
+ * overlapped on three streams.  Synchronous on return. */
+int bgh_logp_grad_host_stream(bgh_ctx* ctx, int32_t n_evals, const double* q, double* logp, double* grad);
+
+/* Layout helpers on the device: chain-major [C][D] <-> gene-major [D][Cp]. */
+int bgh_to_device_layout(bgh_ctx* ctx, const double* q_cd, double* q_dc, void* stream);
+int bgh_from_device_layout(bgh_ctx* ctx, const double* x_dc, double* x_cd, void* stream);
+
+/* Introspection for tests: the SNP-range partition (n_groups+1 offsets into the gene-sorted SNP
+ * array) and kernel launch counters (how many of this library's kernels were launched). */
+int32_t bgh_n_groups(const bgh_ctx* ctx);
+int bgh_get_partition(const bgh_ctx* ctx, int32_t* offsets, int32_t n);
+int32_t bgh_n_split_genes(const bgh_ctx* ctx);
+int64_t bgh_launch_count(const bgh_ctx* ctx);
+/* average device time (ms) of the likelihood kernel since the last call with reset != 0; timing is
+ * only collected after bgh_set_profiling(ctx, 1) (adds CUDA events around each launch). */
+int bgh_set_profiling(bgh_ctx* ctx, int32_t enable);
+int bgh_kernel_time_ms(bgh_ctx* ctx, double* lik_ms, double* finalize_ms, int64_t* n, int32_t reset);
+
+/* Host-only planning (no device needed; used by the CPU tests): gid_sorted[M] ascending compact
+ * gene ids -> offsets[n_groups+1], flags[n_groups] (bit0 head-partial, bit1 tail-partial) and the
+ * CSR of genes whose sum is assembled from slot partials (slot s < n_groups: head slot of group
+ * s; s >= n_groups: tail slot of group s - n_groups).  cap = capacity of the split_* buffers. */
+int bgh_debug_plan(int64_t M, const int32_t* gid_sorted, int32_t G, int32_t n_groups,
+                   int32_t first_partial, int32_t last_partial, int32_t* offsets, int32_t* flags,
+                   int32_t* n_split, int32_t* split_gene, int32_t* split_ptr, int32_t* split_slots,
+                   int32_t cap);
+
+/* FP64 pipe microbenchmark (dependent-free DFMA streams on every SM): returns achieved
+ * G DFMA-lane-instructions / s, the compute roof of the likelihood kernel at large C. */
+int bgh_dfma_peak(bgh_ctx* ctx, double* ginstr_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAGHERA_B200_H */

@@ -1,0 +1,63 @@
+"""CPU tests of the C-ABI boundary: the library loads and exports every declared symbol."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_exports_match_header(built_lib):
+    from baghera_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "baghera_b200.h")).read()
+    declared = set(re.findall(r"\b(bgh_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    for name in declared:
+        assert hasattr(built_lib, name), name
+
+
+def test_version_and_cfg_default(built_lib):
+    from baghera_b200._lib import bgh_cfg, BGH_ABI_VERSION
+    assert b"sm_100a" in built_lib.bgh_version()
+    cfg = bgh_cfg()
+    built_lib.bgh_cfg_default(ctypes.byref(cfg))
+    assert cfg.abi_version == BGH_ABI_VERSION and cfg.first_gene_row == -1 and cfg.n_shared_rows == 0
+    # struct layout must match the header (8-byte aligned fields)
+    assert bgh_cfg.n_snps.offset == 16 and bgh_cfg.c.offset == 32 and ctypes.sizeof(bgh_cfg) == 88
+
+
+def test_create_fails_loudly_without_gpu(built_lib):
+    """No CPU fallback: on a box without a GPU, bgh_create must return BGH_ENODEV with a message."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from baghera_b200._lib import bgh_cfg, BGH_ENODEV
+    cfg = bgh_cfg()
+    built_lib.bgh_cfg_default(ctypes.byref(cfg))
+    cfg.n_snps, cfg.n_genes, cfg.n_chains, cfg.c = 100, 3, 4, 0.28
+    ctx = ctypes.c_void_p()
+    rc = built_lib.bgh_create(ctypes.byref(ctx), ctypes.byref(cfg))
+    assert rc == BGH_ENODEV and not ctx.value
+    assert b"no CPU fallback" in built_lib.bgh_last_error(None)
+
+
+def test_engine_refuses_cpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import numpy as np
+    from baghera_b200.engine import Engine
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Engine(np.ones(8, np.float32), np.ones(8, np.float32), np.zeros(8, np.int32), 1, 0.28, 4)
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under baghera_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "baghera_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
+                assert "liboracle" not in txt, f

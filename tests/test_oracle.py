@@ -1,0 +1,88 @@
+"""CPU tests of the oracle: the four restatements of the reference density agree (SURVEY §8c pins 1-4)."""
+import numpy as np
+import pytest
+
+from baghera_b200 import synth
+from oracle import model_oracle as mo
+from oracle.c_oracle import COracle
+from helpers import grad_rel_err
+
+
+def _inputs(d):
+    return d.chi2.astype(np.float64), d.ld.astype(np.float64), d.gene_id.astype(np.int64)
+
+
+@pytest.mark.parametrize("fix", [False, True])
+def test_four_forms_agree(cfg1, fix):
+    chi2, ld, cat = _inputs(cfg1)
+    ss = mo.SuffStats(chi2, ld, cat, cfg1.G)
+    co = COracle(chi2, ld, cat, cfg1.G, cfg1.c, fix)
+    Q = synth.jittered_start(cfg1.G + 3, 3, seed=11)
+    for q in Q:
+        lp_a, g_a = mo.logp_grad_autograd(q, chi2, ld, cat, cfg1.c, fix)
+        for lp, g in (mo.logp_grad_closed(q, chi2, ld, cat, cfg1.c, fix),
+                      mo.logp_grad_suffstat(q, ss, cfg1.c, fix),
+                      co.logp_grad(q)):
+            assert abs(lp - lp_a) <= 1e-12 * abs(lp_a)
+            assert grad_rel_err(g, g_a) <= 1e-10
+
+
+def test_extreme_transforms(cfg1):
+    """x_W, x_m = +-20, beta < 0, beta huge: closed form == autograd."""
+    chi2, ld, cat = _inputs(cfg1)
+    rng = np.random.default_rng(5)
+    for xW, xm in [(-20.0, 20.0), (20.0, -20.0), (-3.0, 0.0), (5.0, 7.0)]:
+        q = np.concatenate([[xW, 0.3, xm], rng.normal(0.0, 2.0, cfg1.G)])
+        lp_a, g_a = mo.logp_grad_autograd(q, chi2, ld, cat, cfg1.c)
+        lp_b, g_b = mo.logp_grad_closed(q, chi2, ld, cat, cfg1.c)
+        assert np.isfinite(lp_a) and abs(lp_b - lp_a) <= 1e-11 * abs(lp_a)
+        assert grad_rel_err(g_b, g_a) <= 1e-8
+
+
+def test_finite_differences(cfg1):
+    chi2, ld, cat = _inputs(cfg1)
+    q = synth.jittered_start(cfg1.G + 3, 1, seed=2)[0]
+    idx = [0, 1, 2, 3, 50, cfg1.G + 2]
+    fd = mo.finite_difference(lambda x: mo.logp_grad_closed(x, chi2, ld, cat, cfg1.c)[0], q, idx, h=1e-6)
+    _, g = mo.logp_grad_closed(q, chi2, ld, cat, cfg1.c)
+    assert np.allclose(fd, g[idx], rtol=2e-5, atol=1e-4)
+
+
+def test_permutation_invariance(cfg1):
+    """Q6: the reference gathers through an unsorted cat; logp/grad do not depend on SNP order."""
+    chi2, ld, cat = _inputs(cfg1)
+    q = synth.jittered_start(cfg1.G + 3, 1, seed=4)[0]
+    order = np.argsort(cat, kind="stable")
+    lp1, g1 = mo.logp_grad_closed(q, chi2, ld, cat, cfg1.c)
+    lp2, g2 = mo.logp_grad_closed(q, chi2[order], ld[order], cat[order], cfg1.c)
+    assert abs(lp1 - lp2) <= 1e-12 * abs(lp1) and grad_rel_err(g2, g1) <= 1e-10
+
+
+def test_gw_forms_agree():
+    d = synth.make_arrays(30_000, 1, seed=7)
+    chi2, ld = d.chi2.astype(np.float64), d.ld.astype(np.float64)
+    co = COracle(chi2, ld, d.gene_id, 1, d.c)
+    for q in ([1.0, -0.69], [0.2, 3.0], [1.7, -8.0]):
+        a = mo.gw_logp_grad_autograd(q, chi2, ld, d.c)
+        b = mo.gw_logp_grad_closed(q, chi2, ld, d.c)
+        c_ = co.gw_logp_grad(q)
+        for lp, g in (b, c_):
+            assert abs(lp - a[0]) <= 1e-12 * abs(a[0]) and grad_rel_err(g, a[1]) <= 1e-10
+
+
+def test_c_oracle_batch_threads(cfg1):
+    chi2, ld, cat = _inputs(cfg1)
+    co = COracle(chi2, ld, cat, cfg1.G, cfg1.c)
+    Q = synth.jittered_start(cfg1.G + 3, 5, seed=9)
+    lp, g = co.logp_grad_batch(Q, n_threads=3)
+    for i in range(5):
+        l1, g1 = co.logp_grad(Q[i])
+        assert lp[i] == l1 and np.array_equal(g[i], g1)
+
+
+def test_synth_shapes():
+    d = synth.make_arrays(20_000, 200)
+    assert d.M == 20_000 and d.G == 200 and d.chi2.dtype == np.float32 and d.ld.min() >= 1.0
+    counts = np.bincount(d.gene_id, minlength=d.G)
+    assert counts.min() >= 1 and counts[-1] == 9000 and d.gene_names[-1] == "NonCoding"
+    assert abs(d.c - 361194 / 1290028) < 1e-15

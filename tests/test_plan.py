@@ -1,0 +1,65 @@
+"""CPU tests of the host-side work plan (bgh_debug_plan) against an emulation of the kernel's rule."""
+import numpy as np
+import pytest
+
+from baghera_b200 import synth
+from baghera_b200.engine import debug_plan
+from helpers import emulate_plan_gene_sums
+
+
+def _sorted_case(M, G, seed=1):
+    if M == G:   # one SNP per gene
+        rng = np.random.default_rng(seed)
+        return np.arange(G, dtype=np.int32), rng.normal(size=M)
+    d = synth.make_arrays(M, G, seed=seed)
+    order = np.argsort(d.gene_id, kind="stable")
+    return d.gene_id[order].astype(np.int32), d.chi2[order].astype(np.float64)
+
+
+@pytest.mark.parametrize("M,G,NG", [(20_000, 200, 64), (20_000, 200, 2368), (5_000, 1, 300), (300, 7, 1024),
+                                    (1, 1, 16), (4097, 4097, 512), (100_000, 1500, 148 * 16 * 8)])
+def test_plan_covers_and_reassembles(built_lib, M, G, NG):
+    gid, val = _sorted_case(M, G)
+    plan = debug_plan(gid, G, NG)
+    off = plan["off"]
+    assert off[0] == 0 and off[-1] == M and np.all(np.diff(off) >= 0)
+    sums, owners = emulate_plan_gene_sums(plan, gid, val, G)
+    ref = np.bincount(gid, weights=val, minlength=G)
+    assert np.allclose(sums, ref, rtol=1e-12, atol=1e-9)
+    assert np.all(owners == 1), "every gene's prior must be owned by exactly one group"
+
+
+def test_plan_balance_and_snapping(built_lib):
+    gid, _ = _sorted_case(1_100_000, 15_000)
+    NG = 148 * 16
+    plan = debug_plan(gid, 15_000, NG)
+    lens = np.diff(plan["off"])
+    ideal = 1_100_000 / NG
+    assert lens.max() <= 1.15 * ideal and lens.min() >= 0.85 * ideal
+    # a cut is snapped to a gene boundary within ideal/16, so only genes longer than ideal/8 are split
+    counts = np.bincount(gid)
+    assert all(counts[g] > 2 * int(ideal / 16) for g in plan["split_gene"])
+    assert len(plan["split_gene"]) < NG // 4
+    # the long list (NonCoding) comes first
+    n0 = plan["split_ptr"][1] - plan["split_ptr"][0]
+    assert plan["split_gene"][0] == 14_999 and n0 > 1000
+
+
+def test_plan_rank_partial_flags(built_lib):
+    """Sharded ranks: first/last gene continue on neighbours -> they must be assembled from slots."""
+    gid, val = _sorted_case(20_000, 50)
+    plan = debug_plan(gid, 50, 96, first_partial=True, last_partial=True)
+    assert 0 in plan["split_gene"] and 49 in plan["split_gene"]
+    sums, owners = emulate_plan_gene_sums(plan, gid, val, 50)
+    assert np.allclose(sums, np.bincount(gid, weights=val, minlength=50))
+    assert owners[0] == 0 and owners[49] == 1 and np.all(owners[1:49] == 1)
+
+
+def test_plan_rejects_bad_input(built_lib):
+    from baghera_b200._lib import BghError
+    with pytest.raises(BghError):
+        debug_plan(np.array([0, 2, 1], np.int32), 3, 8)      # unsorted
+    with pytest.raises(BghError):
+        debug_plan(np.array([0, 0, 2], np.int32), 3, 8)      # gene 1 missing
+    with pytest.raises(BghError):
+        debug_plan(np.array([0, 5], np.int32), 3, 8)         # id out of range
