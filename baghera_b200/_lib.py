@@ -45,6 +45,32 @@ class bgh_cfg(ctypes.Structure):
     ]
 
 
+class bgh_nuts_buffers(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("state", "ckpt", "sc", "fl", "partials", "sums", "logp_w", "stats",
+                                               "n_active_dev", "n_active_host")]
+
+
+class bgh_nuts_cfg(ctypes.Structure):
+    _fields_ = [
+        ("seed", ctypes.c_uint64),
+        ("target_accept", ctypes.c_double),
+        ("step_scale", ctypes.c_double),
+        ("emax", ctypes.c_double),
+        ("da_gamma", ctypes.c_double),
+        ("da_kappa", ctypes.c_double),
+        ("da_t0", ctypes.c_double),
+        ("n_dim_total", ctypes.c_int32),
+        ("coord_offset", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 4),
+    ]
+
+
+NUTS_MAX_DEPTH, NUTS_N_SLOTS, NUTS_N_SC, NUTS_N_FL, NUTS_N_STATS = 10, 20, 16, 11, 8
+NUTS_MAX_PARTIALS = 1 + 2 * NUTS_MAX_DEPTH
+NUTS_SLOT_Q, NUTS_SLOT_GRAD, NUTS_SLOT_VAR = 0, 1, 2
+NUTS_SLOT_FG_MEAN, NUTS_SLOT_FG_RAW, NUTS_SLOT_BG_MEAN, NUTS_SLOT_BG_RAW = 16, 17, 18, 19
+NUTS_SC_EPS, NUTS_SC_LOGP = 0, 1
+
 _vp = ctypes.c_void_p
 _i32, _i64, _dbl = ctypes.c_int32, ctypes.c_int64, ctypes.c_double
 _pi32 = ctypes.POINTER(ctypes.c_int32)
@@ -77,7 +103,14 @@ SIGNATURES = {
     "bgh_set_profiling": (_i32, [_vp, _i32]),
     "bgh_kernel_time_ms": (_i32, [_vp, _pdbl, _pdbl, _pi64, _i32]),
     "bgh_dfma_peak": (_i32, [_vp, _pdbl]),
-    "bgh_debug_plan": (_i32, [_i64, _pi32, _i32, _i32, _i32, _i32, _pi32, _pi32, _pi32, _pi32, _pi32, _pi32, _i32]),
+    "bgh_nuts_cfg_default": (None, [ctypes.POINTER(bgh_nuts_cfg)]),
+    "bgh_nuts_vec_blocks": (_i32, [_vp]),
+    "bgh_nuts_init": (_i32, [_vp, ctypes.POINTER(bgh_nuts_buffers), ctypes.POINTER(bgh_nuts_cfg), _vp]),
+    "bgh_nuts_transition": (_i32, [_vp, ctypes.POINTER(bgh_nuts_buffers), ctypes.POINTER(bgh_nuts_cfg), _i64, _i32, _i32,
+                                   _dbl, _dbl, _i32, _vp, _pi32]),
+    "bgh_nuts_stop_tuning": (_i32, [_vp, ctypes.POINTER(bgh_nuts_buffers), ctypes.POINTER(bgh_nuts_cfg), _vp]),
+    "bgh_debug_trace": (_i32, [_vp, _i32, _vp, _i64]),
+    "bgh_debug_plan": (_i32, [_i64, _pi32, _i32, _i32, _i32, _i32, _i32, _pi32, _pi32, _pi32, _pi32, _pi32, _pi32, _i32]),
 }
 
 _LIB = None

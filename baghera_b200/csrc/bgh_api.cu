@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -10,16 +11,19 @@
 #include <vector>
 
 #include "bgh_internal.h"
+#include "bgh_sampler.h"
 
 namespace bgh {
 
 // ---------------------------------------------------------------------------------------------
 // work planning (pure host code)
 // ---------------------------------------------------------------------------------------------
-int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_groups, bool first_partial,
-               bool last_partial, int first_row, int last_row, Plan* plan, std::string* err)
+int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_cta, int groups_per_cta,
+               bool first_partial, bool last_partial, int first_row, int last_row, double kappa,
+               Plan* plan, std::string* err)
 {
-    if (M < 0 || M > 0x7fffff00LL || n_groups <= 0 || G <= 0) {
+    const int n_groups = n_cta * groups_per_cta;
+    if (M < 0 || M > 0x7fffff00LL || n_cta <= 0 || groups_per_cta <= 0 || G <= 0) {
         *err = "build_plan: bad sizes";
         return BGH_EINVAL;
     }
@@ -48,35 +52,74 @@ int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_groups, bool firs
     Plan& P = *plan;
     P = Plan();
     P.n_groups = n_groups;
+    P.n_cta = n_cta;
     P.off.assign((size_t)n_groups + 1, 0);
     P.flags.assign((size_t)n_groups, 0);
 
-    // cuts: ideal equal-SNP cuts snapped to the nearest gene boundary when one lies within
-    // 1/16 of a range length, so that only genes longer than a range are ever split.
-    const double len = (double)M / (double)n_groups;
-    const int64_t tol = (int64_t)floor(len / 16.0);
-    P.off[0] = 0;
-    P.off[(size_t)n_groups] = (int32_t)M;
-    for (int k = 1; k < n_groups; ++k) {
-        int64_t x = (int64_t)llround((double)k * len);
-        if (x < P.off[(size_t)k - 1]) x = P.off[(size_t)k - 1];
-        if (x > M) x = M;
-        if (tol > 0) {
-            // nearest gene boundary to x
-            auto it = std::lower_bound(goff.begin(), goff.end(), (int32_t)x);
-            int64_t best = -1;
-            if (it != goff.end() && llabs((int64_t)*it - x) <= tol) best = *it;
-            if (it != goff.begin()) {
-                const int64_t lo = *(it - 1);
-                if (llabs(lo - x) <= tol && (best < 0 || llabs(lo - x) < llabs(best - x))) best = lo;
+    // ---- regions: a "huge" gene (>= 1.5 CTAs' worth of SNPs, e.g. NonCoding = 45% of all SNPs)
+    // gets CTAs of its own, whose groups all accumulate the same gene and are reduced inside the
+    // CTA (one partial per CTA instead of one per group); maximal runs of the other genes form
+    // "mixed" regions.  CTAs are apportioned to regions by cost = SNPs + kappa * gene boundaries
+    // (a boundary costs a flush + a slope reload, about kappa SNPs' worth of issue slots).
+    struct Region { int64_t a, b; int32_t gene; int n; int32_t g0, g1; double w; };   // gene = -1 for mixed
+    std::vector<Region> regions;
+    if (!(kappa >= 0.0)) kappa = 0.0;
+    const double per_cta = (double)M / (double)n_cta;
+    {
+        int64_t run_start = 0;
+        int32_t run_g = 0;
+        for (int32_t g = 0; g < G; ++g) {
+            const int64_t sz = goff[(size_t)g + 1] - goff[g];
+            if (n_cta > 1 && (double)sz >= 1.5 * per_cta && sz >= 4 * (int64_t)groups_per_cta) {
+                if (goff[g] > run_start) regions.push_back({run_start, goff[g], -1, 0, run_g, g, 0.0});
+                regions.push_back({goff[g], goff[(size_t)g + 1], g, 0, g, g + 1, 0.0});
+                run_start = goff[(size_t)g + 1];
+                run_g = g + 1;
             }
-            if (best >= P.off[(size_t)k - 1]) x = best;
         }
-        P.off[(size_t)k] = (int32_t)x;
+        if (M > run_start || regions.empty()) regions.push_back({run_start, M, -1, 0, run_g, G, 0.0});
+        if ((int)regions.size() > n_cta) {   // degenerate (tiny n_cta): one mixed region
+            regions.clear();
+            regions.push_back({0, M, -1, 0, 0, G, 0.0});
+        }
+    }
+    {
+        double w_total = 0.0;
+        for (auto& r : regions) {
+            r.w = (double)(r.b - r.a) + (r.gene >= 0 ? 0.0 : kappa * (double)(r.g1 - r.g0));
+            w_total += r.w;
+        }
+        const double w_per_cta = std::max(w_total / (double)n_cta, 1e-9);
+        int total = 0;
+        for (auto& r : regions) {
+            r.n = std::max(1, (int)llround(r.w / w_per_cta));
+            total += r.n;
+        }
+        while (total > n_cta) {   // take from the most over-provisioned region
+            int best = -1;
+            double best_v = -1.0;
+            for (size_t i = 0; i < regions.size(); ++i) {
+                if (regions[i].n <= 1) continue;
+                const double v = (double)regions[i].n / std::max(regions[i].w, 1e-9);
+                if (v > best_v) { best_v = v; best = (int)i; }
+            }
+            regions[(size_t)best].n--;
+            total--;
+        }
+        while (total < n_cta) {   // give to the most loaded region
+            int best = 0;
+            double best_v = -1.0;
+            for (size_t i = 0; i < regions.size(); ++i) {
+                const double v = regions[i].w / (double)regions[i].n;
+                if (v > best_v) { best_v = v; best = (int)i; }
+            }
+            regions[(size_t)best].n++;
+            total++;
+        }
     }
 
-    // flags + slot lists, mirroring the kernel's flush rule
-    std::vector<std::vector<int32_t>> lists;       // per split gene, in discovery (= gene) order
+    // ---- group ranges
+    std::vector<std::vector<int32_t>> lists;   // per split gene, in gene order
     std::vector<int32_t> list_gene;
     auto add_slot = [&](int32_t gene, int32_t slot) {
         if (list_gene.empty() || list_gene.back() != gene) {
@@ -85,15 +128,105 @@ int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_groups, bool firs
         }
         lists.back().push_back(slot);
     };
+    int v0 = 0, cta0 = 0;
+    for (const Region& r : regions) {
+        const int ng = r.n * groups_per_cta;
+        const double len = (double)(r.b - r.a) / (double)ng;
+        if (r.gene >= 0) {
+            // exclusive CTAs: equal cuts, every group flagged kExclusive; one slot per CTA
+            const bool owned_here = !(r.gene == 0 && first_partial);
+            for (int k = 0; k < ng; ++k) {
+                const int64_t x = r.a + (int64_t)llround((double)k * len);
+                P.off[(size_t)(v0 + k)] = (int32_t)x;
+                P.flags[(size_t)(v0 + k)] = kExclusive;
+            }
+            // the prior terms of the gene belong to the (first non-empty) group holding its first SNP
+            for (int k = 0; k < ng && owned_here; ++k) {
+                const int64_t xa = P.off[(size_t)(v0 + k)];
+                const int64_t xb = (k + 1 < ng) ? (int64_t)P.off[(size_t)(v0 + k + 1)] : r.b;
+                if (xb > xa) {
+                    P.flags[(size_t)(v0 + k)] |= kOwner;
+                    break;
+                }
+            }
+            for (int c = 0; c < r.n; ++c) add_slot(r.gene, 2 * n_groups + cta0 + c);
+        } else {
+            // mixed region: ideal equal cuts snapped to the nearest gene boundary within len/16, so
+            // that only genes longer than len/8 are ever split across groups
+            const int64_t tol = (int64_t)floor(len / 16.0);
+            int64_t prev = r.a;
+            // cost of [r.a, x): SNPs + kappa * genes started; cuts equalise the cost
+            auto cost = [&](int64_t x) {
+                const int64_t ng_started = std::lower_bound(goff.begin() + r.g0, goff.begin() + r.g1, (int32_t)x) - (goff.begin() + r.g0);
+                return (double)(x - r.a) + kappa * (double)ng_started;
+            };
+            for (int k = 0; k < ng; ++k) {
+                int64_t x;
+                {
+                    const double target = r.w * (double)k / (double)ng;
+                    int64_t lo = r.a, hi = r.b;
+                    while (lo < hi) {
+                        const int64_t mid = lo + (hi - lo) / 2;
+                        if (cost(mid) < target) lo = mid + 1; else hi = mid;
+                    }
+                    x = lo;
+                }
+                if (k == 0) x = r.a;
+                if (x < prev) x = prev;
+                if (x > r.b) x = r.b;
+                if (k > 0 && tol > 0) {
+                    auto it = std::lower_bound(goff.begin(), goff.end(), (int32_t)x);
+                    int64_t best = -1;
+                    if (it != goff.end() && llabs((int64_t)*it - x) <= tol) best = *it;
+                    if (it != goff.begin()) {
+                        const int64_t lo = *(it - 1);
+                        if (llabs(lo - x) <= tol && (best < 0 || llabs(lo - x) < llabs(best - x))) best = lo;
+                    }
+                    if (best >= prev && best <= r.b) x = best;
+                }
+                P.off[(size_t)(v0 + k)] = (int32_t)x;
+                prev = x;
+            }
+        }
+        v0 += ng;
+        cta0 += r.n;
+        P.off[(size_t)v0] = (int32_t)r.b;
+    }
+    P.off[(size_t)n_groups] = (int32_t)M;
+
+    // flags + slot lists of the mixed groups, mirroring the kernel's flush rule
+    std::vector<std::pair<int32_t, int32_t>> mixed_slots;   // (gene, slot)
     for (int v = 0; v < n_groups; ++v) {
+        if (P.flags[(size_t)v] & kExclusive) continue;
         const int32_t a = P.off[(size_t)v], b = P.off[(size_t)v + 1];
         if (a >= b) continue;
         const int32_t gf = gid[a], gl = gid[b - 1];
         const bool head = (a > 0) ? (gid[a - 1] == gf) : first_partial;
         const bool tail = (b < M) ? (gid[b] == gl) : last_partial;
         P.flags[(size_t)v] = (head ? kHeadPartial : 0) | (tail ? kTailPartial : 0);
-        if (head) add_slot(gf, v);
-        if (tail && !(gl == gf && head)) add_slot(gl, n_groups + v);
+        if (head) mixed_slots.emplace_back(gf, v);
+        if (tail && !(gl == gf && head)) mixed_slots.emplace_back(gl, n_groups + v);
+    }
+    // merge exclusive lists and mixed slots in gene order (a gene is either exclusive or mixed)
+    {
+        std::vector<std::vector<int32_t>> all_lists;
+        std::vector<int32_t> all_gene;
+        size_t ie = 0, im = 0;
+        while (ie < lists.size() || im < mixed_slots.size()) {
+            const int32_t ge = ie < lists.size() ? list_gene[ie] : INT32_MAX;
+            const int32_t gm = im < mixed_slots.size() ? mixed_slots[im].first : INT32_MAX;
+            if (ge <= gm) {
+                all_gene.push_back(ge);
+                all_lists.push_back(lists[ie]);
+                ++ie;
+            } else {
+                all_gene.push_back(gm);
+                all_lists.emplace_back();
+                while (im < mixed_slots.size() && mixed_slots[im].first == gm) all_lists.back().push_back(mixed_slots[im++].second);
+            }
+        }
+        lists.swap(all_lists);
+        list_gene.swap(all_gene);
     }
     // long lists first (one CTA each in finalize), then the short ones (one warp each)
     std::vector<size_t> order;
@@ -110,7 +243,7 @@ int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_groups, bool firs
         if (g == 0 && first_partial) row = first_row;
         if (g == G - 1 && last_partial && last_row >= 0) row = last_row;
         P.split_row.push_back(row);
-        for (int32_t s : lists[i]) P.split_slots.push_back(s);
+        for (int32_t sl : lists[i]) P.split_slots.push_back(sl);
         P.split_ptr.push_back((int32_t)P.split_slots.size());
     }
     return BGH_OK;
@@ -141,10 +274,12 @@ struct bgh_ctx {
     double* d_slots = nullptr;
     double* d_part = nullptr;
     double* d_payload = nullptr;
+    double* d_cc = nullptr;
     int* d_split_gene = nullptr;
     int* d_split_row = nullptr;
     int* d_split_ptr = nullptr;
     int* d_split_slots = nullptr;
+    unsigned long long* d_trace = nullptr;   // tools only (bgh_debug_trace)
     // host-entry staging (lazily allocated)
     static constexpr int kPipe = 2;
     double* d_q_cd[kPipe] = {nullptr, nullptr};
@@ -180,6 +315,14 @@ static int fail(bgh_ctx* ctx, int code, const std::string& msg)
             return fail(ctx, BGH_ECUDA, _buf);                                                 \
         }                                                                                      \
     } while (0)
+
+// cost of one gene boundary in SNP-equivalents for the work plan (BGH_PLAN_KAPPA overrides; tuning only)
+static double plan_kappa()
+{
+    const char* e = getenv("BGH_PLAN_KAPPA");
+    if (e && *e) return atof(e);
+    return 10.0;
+}
 
 static void pick_chain_geometry(int C, int* CL, int* CPL, int* Cp)
 {
@@ -270,7 +413,8 @@ void bgh_destroy(bgh_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     cudaFree(ctx->d_chi2); cudaFree(ctx->d_ld); cudaFree(ctx->d_gid); cudaFree(ctx->d_groups);
-    cudaFree(ctx->d_slots); cudaFree(ctx->d_part); cudaFree(ctx->d_payload);
+    cudaFree(ctx->d_slots); cudaFree(ctx->d_part); cudaFree(ctx->d_payload); cudaFree(ctx->d_cc);
+    cudaFree(ctx->d_trace);
     cudaFree(ctx->d_split_gene); cudaFree(ctx->d_split_row); cudaFree(ctx->d_split_ptr); cudaFree(ctx->d_split_slots);
     for (int i = 0; i < bgh_ctx::kPipe; ++i) {
         cudaFree(ctx->d_q_cd[i]); cudaFree(ctx->d_q_dc[i]); cudaFree(ctx->d_g_dc[i]); cudaFree(ctx->d_g_cd[i]);
@@ -305,15 +449,15 @@ int bgh_get_partition(const bgh_ctx* ctx, int32_t* offsets, int32_t n)
 
 // Host-only planning entry point used by the CPU tests (no device needed): sorted gene ids in,
 // offsets[n_groups+1], flags[n_groups] out; split CSR returned through caller-sized buffers.
-int bgh_debug_plan(int64_t M, const int32_t* gid_sorted, int32_t G, int32_t n_groups, int32_t first_partial,
+int bgh_debug_plan(int64_t M, const int32_t* gid_sorted, int32_t G, int32_t n_cta, int32_t groups_per_cta, int32_t first_partial,
                    int32_t last_partial, int32_t* offsets, int32_t* flags, int32_t* n_split,
                    int32_t* split_gene, int32_t* split_ptr, int32_t* split_slots, int32_t cap)
 {
     Plan P;
     std::string err;
-    int rc = build_plan(M, gid_sorted, G, n_groups, first_partial != 0, last_partial != 0,
+    int rc = build_plan(M, gid_sorted, G, n_cta, groups_per_cta, first_partial != 0, last_partial != 0,
                         first_partial ? 0 : -1, last_partial ? (first_partial && G == 1 ? 0 : (first_partial ? 1 : 0)) : -1,
-                        &P, &err);
+                        plan_kappa(), &P, &err);
     if (rc != BGH_OK) return fail(nullptr, rc, err);
     memcpy(offsets, P.off.data(), sizeof(int32_t) * P.off.size());
     memcpy(flags, P.flags.data(), sizeof(int32_t) * P.flags.size());
@@ -323,6 +467,29 @@ int bgh_debug_plan(int64_t M, const int32_t* gid_sorted, int32_t G, int32_t n_gr
     memcpy(split_gene, P.split_gene.data(), sizeof(int32_t) * (size_t)ns);
     memcpy(split_ptr, P.split_ptr.data(), sizeof(int32_t) * (size_t)(ns + 1));
     memcpy(split_slots, P.split_slots.data(), sizeof(int32_t) * P.split_slots.size());
+    return BGH_OK;
+}
+
+// Tools only: enable (buf != NULL -> allocate) per-warp phase timestamps of the likelihood kernel and
+// copy the last launch's trace [chain_blocks * n_cta * 16 warps][8] u64 to `out` (may be NULL).
+int bgh_debug_trace(bgh_ctx* ctx, int32_t enable, uint64_t* out, int64_t n_words)
+{
+    if (!ctx) return BGH_EINVAL;
+    BGH_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t words = (size_t)ctx->chain_blocks * ctx->n_cta * kLikWarps * 8;
+    if (enable && !ctx->d_trace) {
+        BGH_CUDA(ctx, cudaMalloc(&ctx->d_trace, words * sizeof(unsigned long long)));
+        BGH_CUDA(ctx, cudaMemset(ctx->d_trace, 0, words * sizeof(unsigned long long)));
+    }
+    if (out) {
+        if (!ctx->d_trace || (size_t)n_words != words) return fail(ctx, BGH_EINVAL, "bgh_debug_trace: bad buffer size");
+        BGH_CUDA(ctx, cudaDeviceSynchronize());
+        BGH_CUDA(ctx, cudaMemcpy(out, ctx->d_trace, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    }
+    if (!enable && ctx->d_trace) {
+        cudaFree(ctx->d_trace);
+        ctx->d_trace = nullptr;
+    }
     return BGH_OK;
 }
 
@@ -372,19 +539,20 @@ int bgh_upload(bgh_ctx* ctx, const float* chi2, const float* ld, const int32_t* 
     const bool fp = gw ? true : ctx->cfg.first_gene_partial != 0;
     const bool lp = gw ? true : ctx->cfg.last_gene_partial != 0;
     std::string err;
-    int rc = build_plan(M, g_sorted.data(), G, ctx->n_groups, fp, lp, ctx->cfg.first_gene_row,
-                        ctx->cfg.last_gene_row, &ctx->plan, &err);
+    int rc = build_plan(M, g_sorted.data(), G, ctx->n_cta, kLikWarps * (32 / ctx->CL), fp, lp, ctx->cfg.first_gene_row,
+                        ctx->cfg.last_gene_row, plan_kappa(), &ctx->plan, &err);
     if (rc != BGH_OK) return fail(ctx, rc, err);
 
     auto dfree = [](auto*& p) { cudaFree(p); p = nullptr; };
     dfree(ctx->d_chi2); dfree(ctx->d_ld); dfree(ctx->d_gid); dfree(ctx->d_groups); dfree(ctx->d_slots);
-    dfree(ctx->d_part); dfree(ctx->d_payload); dfree(ctx->d_split_gene); dfree(ctx->d_split_row);
+    dfree(ctx->d_part); dfree(ctx->d_payload); dfree(ctx->d_cc); dfree(ctx->d_split_gene); dfree(ctx->d_split_row);
     dfree(ctx->d_split_ptr); dfree(ctx->d_split_slots);
 
     const Plan& P = ctx->plan;
     std::vector<int4> groups((size_t)ctx->n_groups);
     for (int v = 0; v < ctx->n_groups; ++v)
-        groups[(size_t)v] = make_int4(P.off[(size_t)v], P.off[(size_t)v + 1], P.flags[(size_t)v], 0);
+        groups[(size_t)v] = make_int4(P.off[(size_t)v], P.off[(size_t)v + 1], P.flags[(size_t)v],
+                                      P.off[(size_t)v] < P.off[(size_t)v + 1] ? g_sorted[(size_t)P.off[(size_t)v]] : 0);
     const size_t ns = P.split_gene.size();
     const size_t nsl = std::max<size_t>(P.split_slots.size(), 1);
 
@@ -392,8 +560,9 @@ int bgh_upload(bgh_ctx* ctx, const float* chi2, const float* ld, const int32_t* 
     BGH_CUDA(ctx, cudaMalloc(&ctx->d_ld, sizeof(float) * (size_t)Mpad));
     BGH_CUDA(ctx, cudaMalloc(&ctx->d_gid, sizeof(int) * (size_t)Mpad));
     BGH_CUDA(ctx, cudaMalloc(&ctx->d_groups, sizeof(int4) * groups.size()));
-    BGH_CUDA(ctx, cudaMalloc(&ctx->d_slots, sizeof(double) * 2 * (size_t)ctx->n_groups * ctx->Cp));
+    BGH_CUDA(ctx, cudaMalloc(&ctx->d_slots, sizeof(double) * (2 * (size_t)ctx->n_groups + ctx->n_cta) * ctx->Cp));
     BGH_CUDA(ctx, cudaMalloc(&ctx->d_part, sizeof(double) * 4 * (size_t)ctx->n_cta * ctx->Cp));
+    BGH_CUDA(ctx, cudaMalloc(&ctx->d_cc, sizeof(double) * 2 * (size_t)ctx->Cp));
     BGH_CUDA(ctx, cudaMalloc(&ctx->d_payload, sizeof(double) * (size_t)(4 + ctx->cfg.n_shared_rows) * ctx->Cp));
     BGH_CUDA(ctx, cudaMalloc(&ctx->d_split_gene, sizeof(int) * std::max<size_t>(ns, 1)));
     BGH_CUDA(ctx, cudaMalloc(&ctx->d_split_row, sizeof(int) * std::max<size_t>(ns, 1)));
@@ -403,7 +572,7 @@ int bgh_upload(bgh_ctx* ctx, const float* chi2, const float* ld, const int32_t* 
     BGH_CUDA(ctx, cudaMemcpy(ctx->d_ld, l_sorted.data(), sizeof(float) * (size_t)Mpad, cudaMemcpyHostToDevice));
     BGH_CUDA(ctx, cudaMemcpy(ctx->d_gid, g_sorted.data(), sizeof(int) * (size_t)Mpad, cudaMemcpyHostToDevice));
     BGH_CUDA(ctx, cudaMemcpy(ctx->d_groups, groups.data(), sizeof(int4) * groups.size(), cudaMemcpyHostToDevice));
-    BGH_CUDA(ctx, cudaMemset(ctx->d_slots, 0, sizeof(double) * 2 * (size_t)ctx->n_groups * ctx->Cp));
+    BGH_CUDA(ctx, cudaMemset(ctx->d_slots, 0, sizeof(double) * (2 * (size_t)ctx->n_groups + ctx->n_cta) * ctx->Cp));
     BGH_CUDA(ctx, cudaMemset(ctx->d_payload, 0, sizeof(double) * (size_t)(4 + ctx->cfg.n_shared_rows) * ctx->Cp));
     if (ns) {
         BGH_CUDA(ctx, cudaMemcpy(ctx->d_split_gene, P.split_gene.data(), sizeof(int) * ns, cudaMemcpyHostToDevice));
@@ -419,10 +588,10 @@ static void fill_params(bgh_ctx* ctx, const double* q, double* grad, double* log
                         LikParams* lp, FinParams* fp)
 {
     lp->chi2 = ctx->d_chi2; lp->ld = ctx->d_ld; lp->gid = ctx->d_gid; lp->groups = ctx->d_groups;
-    lp->q = q; lp->grad = grad; lp->slots = ctx->d_slots; lp->part = ctx->d_part;
+    lp->q = q; lp->grad = grad; lp->slots = ctx->d_slots; lp->part = ctx->d_part; lp->cc = ctx->d_cc; lp->trace = ctx->d_trace;
     lp->Cp = ctx->Cp; lp->G = ctx->cfg.n_genes; lp->NG = ctx->n_groups; lp->model = ctx->cfg.model;
     lp->fix = ctx->cfg.fix_intercept; lp->c = ctx->cfg.c;
-    fp->q = q; fp->grad = grad; fp->logp = logp; fp->slots = ctx->d_slots; fp->part = ctx->d_part;
+    fp->q = q; fp->grad = grad; fp->logp = logp; fp->slots = ctx->d_slots; fp->part = ctx->d_part; fp->cc = ctx->d_cc;
     fp->payload = payload;
     fp->split_gene = ctx->d_split_gene; fp->split_row = ctx->d_split_row; fp->split_ptr = ctx->d_split_ptr;
     fp->split_slots = ctx->d_split_slots; fp->n_split = (int)ctx->plan.split_gene.size(); fp->n_long = ctx->plan.n_long;
@@ -625,6 +794,123 @@ int bgh_dfma_peak(bgh_ctx* ctx, double* ginstr_per_s)
     cudaEventDestroy(e1);
     cudaFree(d_out);
     *ginstr_per_s = best;
+    return BGH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched NUTS: host-side transition loop
+// ---------------------------------------------------------------------------------------------
+void bgh_nuts_cfg_default(bgh_nuts_cfg* cfg)
+{
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->seed = 20211;
+    cfg->target_accept = 0.90;
+    cfg->step_scale = 0.25;
+    cfg->emax = 1000.0;
+    cfg->da_gamma = 0.05;
+    cfg->da_kappa = 0.75;
+    cfg->da_t0 = 10.0;
+}
+
+int32_t bgh_nuts_vec_blocks(const bgh_ctx* ctx) { return ctx ? 2 * ctx->sm_count : 0; }
+
+static int nuts_params(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nuts_cfg* cfg, int64_t draw, NutsParams* p)
+{
+    if (!ctx || !buf || !cfg) return fail(ctx, BGH_EINVAL, "bgh_nuts: null argument");
+    if (!ctx->uploaded) return fail(ctx, BGH_ESTATE, "bgh_nuts: call bgh_upload first");
+    if (ctx->cfg.n_shared_rows != 0) return fail(ctx, BGH_ESTATE, "bgh_nuts: the device sampler runs on single-rank contexts");
+    if (!buf->state || !buf->ckpt || !buf->sc || !buf->fl || !buf->partials || !buf->sums || !buf->logp_w ||
+        !buf->n_active_dev || !buf->n_active_host)
+        return fail(ctx, BGH_EINVAL, "bgh_nuts: null buffer");
+    p->state = buf->state; p->ckpt = buf->ckpt; p->sc = buf->sc; p->fl = buf->fl; p->partials = buf->partials;
+    p->sums = buf->sums; p->logp_w = buf->logp_w; p->n_active = buf->n_active_dev;
+    p->D = ctx->D; p->Cp = ctx->Cp; p->C = ctx->cfg.n_chains; p->n_vec_blocks = 2 * ctx->sm_count;
+    p->coord_offset = cfg->coord_offset; p->seed = cfg->seed; p->draw = draw;
+    p->emax = cfg->emax; p->target_accept = cfg->target_accept; p->da_gamma = cfg->da_gamma;
+    p->da_kappa = cfg->da_kappa; p->da_t0 = cfg->da_t0;
+    return BGH_OK;
+}
+
+int bgh_nuts_init(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nuts_cfg* cfg, void* stream)
+{
+    NutsParams p;
+    int rc = nuts_params(ctx, buf, cfg, 0, &p);
+    if (rc != BGH_OK) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t vec = (size_t)ctx->D * ctx->Cp;
+    rc = run_local(ctx, buf->state + kSlotQP * vec, buf->logp_w, buf->state + kSlotGP * vec, ctx->d_payload, true, s);
+    if (rc != BGH_OK) return rc;
+    const int Dtot = cfg->n_dim_total > 0 ? cfg->n_dim_total : ctx->D;
+    const double step0 = cfg->step_scale / pow((double)Dtot, 0.25);
+    BGH_CUDA(ctx, nuts_launch_init(p, step0, s));
+    ctx->launches += 1;
+    return BGH_OK;
+}
+
+int bgh_nuts_stop_tuning(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nuts_cfg* cfg, void* stream)
+{
+    NutsParams p;
+    int rc = nuts_params(ctx, buf, cfg, 0, &p);
+    if (rc != BGH_OK) return rc;
+    BGH_CUDA(ctx, nuts_launch_stop_tuning(p, (cudaStream_t)stream));
+    ctx->launches += 1;
+    return BGH_OK;
+}
+
+int bgh_nuts_transition(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nuts_cfg* cfg, int64_t draw,
+                        int32_t tune, int32_t max_treedepth, double fg_weight, double bg_weight,
+                        int32_t switch_window, void* stream, int32_t* n_leapfrogs)
+{
+    NutsParams p;
+    int rc = nuts_params(ctx, buf, cfg, draw, &p);
+    if (rc != BGH_OK) return rc;
+    if (max_treedepth < 1 || max_treedepth > kNutsMaxDepth) return fail(ctx, BGH_EINVAL, "bgh_nuts_transition: bad max_treedepth");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t vec = (size_t)ctx->D * ctx->Cp;
+    double* const qw = buf->state + kSlotQW * vec;
+    double* const gw = buf->state + kSlotGW * vec;
+    int leapfrogs = 0;
+
+    BGH_CUDA(ctx, nuts_launch_begin(p, s));
+    ctx->launches += 2;
+    for (int depth = 0; depth < max_treedepth; ++depth) {
+        BGH_CUDA(ctx, nuts_launch_dir(p, s));
+        ctx->launches += 1;
+        const int n_leaves = 1 << depth;
+        for (int leaf = 0; leaf < n_leaves; ++leaf) {
+            BGH_CUDA(ctx, nuts_launch_leap1(p, leaf == 0 ? 1 : 0, s));
+            rc = run_local(ctx, qw, buf->logp_w, gw, ctx->d_payload, true, s);
+            if (rc != BGH_OK) return rc;
+            // checkpoint bookkeeping of the iterative tree (see bgh_sampler.cu)
+            int idx_max = 0;
+            for (int x = leaf >> 1; x > 0; x >>= 1) idx_max += x & 1;
+            int store_level = -1, lvl_min = 0, lvl_max = -1;
+            if ((leaf & 1) == 0) {
+                store_level = idx_max;
+            } else {
+                int ones = 0;
+                for (int x = leaf; x & 1; x >>= 1) ++ones;
+                lvl_max = idx_max;
+                lvl_min = idx_max - ones + 1;
+            }
+            BGH_CUDA(ctx, nuts_launch_leap2(p, leaf, store_level, lvl_min, lvl_max, s));
+            ctx->launches += kNutsLaunchesPerLeaf;
+            ++leapfrogs;
+        }
+        BGH_CUDA(ctx, nuts_launch_end_doubling(p, max_treedepth, s));
+        ctx->launches += 3;
+        BGH_CUDA(ctx, cudaMemcpyAsync(buf->n_active_host, buf->n_active_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        BGH_CUDA(ctx, cudaStreamSynchronize(s));
+        if (*buf->n_active_host <= 0) break;
+    }
+    if (tune) {
+        BGH_CUDA(ctx, nuts_launch_adapt_mass(p, fg_weight, bg_weight, switch_window, s));
+        ctx->launches += 1;
+    }
+    BGH_CUDA(ctx, nuts_launch_finish(p, tune, buf->stats, s));
+    ctx->launches += 1;
+    if (n_leapfrogs) *n_leapfrogs = leapfrogs;
     return BGH_OK;
 }
 

@@ -15,11 +15,16 @@ namespace bgh {
 constexpr int kLikThreads = 512;               // one CTA per SM, 16 warps
 constexpr int kLikWarps = kLikThreads / 32;
 constexpr int kChunk = 128;                    // SNPs staged per warp per chunk
+#ifndef BGH_LIK_BATCH
+#define BGH_LIK_BATCH 8
+#endif
+constexpr int kLikBatch = BGH_LIK_BATCH;       // SNPs per branch-free inner-loop batch
 constexpr int kFinThreads = 1024;
+constexpr int kFinConstChains = 128;           // chains closed per pass of finalize CTA 0
 constexpr int kShortSplit = 32;                // split lists up to this length are summed by one warp
 constexpr double kLog2Pi = 1.8378770664093454835606594728112;
 
-enum : int { kHeadPartial = 1, kTailPartial = 2 };
+enum : int { kHeadPartial = 1, kTailPartial = 2, kExclusive = 4, kOwner = 8 };
 
 // Work decomposition of the gene-sorted SNP array (host side, no CUDA needed).
 // A "group" is CL consecutive lanes of a warp that walk one contiguous SNP range
@@ -27,11 +32,13 @@ enum : int { kHeadPartial = 1, kTailPartial = 2 };
 // sequential fp64 accumulations (deterministic, no atomics).
 struct Plan {
     int n_groups = 0;
+    int n_cta = 0;
     std::vector<int32_t> off;          // [n_groups+1] range offsets
     std::vector<int32_t> flags;        // [n_groups]   kHeadPartial | kTailPartial
     // genes whose sum is assembled from slot partials: CSR over slot indices.
-    // slot index s < n_groups  : head slot of group s
-    // slot index s >= n_groups : tail slot of group s - n_groups
+    // slot index s <  n_groups              : head slot of group s
+    // slot index n_groups <= s < 2 n_groups : tail slot of group s - n_groups
+    // slot index s >= 2 n_groups            : CTA slot of likelihood CTA s - 2 n_groups (exclusive CTAs)
     int n_long = 0;                    // split genes with > kShortSplit slots come first
     std::vector<int32_t> split_gene;   // [ns]
     std::vector<int32_t> split_row;    // [ns] payload row (>=0) if the gene is rank-shared, else -1
@@ -40,18 +47,21 @@ struct Plan {
 };
 
 // gid must be sorted ascending.  Returns 0 or BGH_EINVAL (message in err).
-int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_groups, bool first_partial,
-               bool last_partial, int first_row, int last_row, Plan* plan, std::string* err);
+int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_cta, int groups_per_cta,
+               bool first_partial, bool last_partial, int first_row, int last_row, double kappa,
+               Plan* plan, std::string* err);
 
 struct LikParams {
     const float* chi2;
     const float* ld;
     const int* gid;
-    const int4* groups;   // {a, b, flags, 0}
+    const int4* groups;   // {a, b, flags, gene id of SNP a}
     const double* q;      // [D][Cp]
     double* grad;         // [D][Cp]
-    double* slots;        // [2*NG][Cp]
+    double* slots;        // [2*NG + nCTA][Cp]
     double* part;         // [nCTA][4][Cp]
+    double* cc;           // [2][Cp] per-chain constants {1/W^2, mi} written for finalize
+    unsigned long long* trace;   // optional [chain_blocks*nCTA*kLikWarps][8] phase timestamps, or NULL
     int Cp;
     int G;
     int NG;
@@ -66,6 +76,7 @@ struct FinParams {
     double* logp;
     const double* slots;
     const double* part;
+    const double* cc;     // [2][Cp] from the likelihood kernel
     double* payload;      // [(4+n_shared)][Cp]
     const int* split_gene;
     const int* split_row;

@@ -71,36 +71,55 @@ __device__ __forceinline__ double log1m_sigmoid_d(double x)
 constexpr double kGwFixLo = 0.9999;
 constexpr double kGwFixHi = 1.0000001;
 
-struct __align__(16) SnpA {
-    double s;    // chi2
-    double nl;   // -ld
-};
-struct __align__(16) SnpB {
-    double w;    // 1/ld
-    int g;       // gene id
-    int pad;
-};
+// Warp-private staging area, structure of arrays: s[kStride] (chi2), nl[kStride] (-ld), w[kStride]
+// (1/ld) as fp64 and g[kStride] (gene id).  Group grp of a warp owns elements [grp*(CH+2), +CH): the
+// +2 doubles of padding shift consecutive groups by 16 bytes so that the per-group broadcast
+// LDS.128 of the SL groups fall into different banks.
+constexpr int kStride = kChunk + 2 * 8;    // fp64 arrays: up to 8 groups per warp, +2 doubles each
+constexpr int kStrideG = kChunk + 4 * 8;   // gene ids: +4 ints per group keeps the int4 stores aligned
+constexpr size_t kWarpStageBytes = (size_t)kStride * 3 * sizeof(double) + (size_t)kStrideG * sizeof(int);
+static_assert(kWarpStageBytes % 16 == 0, "warp staging area must keep 16-byte alignment");
 
 size_t lik_smem_bytes()
 {
-    const size_t stage = (size_t)kLikWarps * kChunk * (sizeof(SnpA) + sizeof(SnpB));
-    return stage;  // the end-of-kernel reduction reuses the staging area
+    const size_t stage = (size_t)kLikWarps * kWarpStageBytes;
+    const size_t red = (size_t)kLikWarps * 5 * 64 * sizeof(double);   // epilogue reduction reuses the area
+    return stage > red ? stage : red;
 }
 
 // ---------------------------------------------------------------------------------------------
 // K1: fused likelihood + gradient
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned sm_id()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
+// optional per-warp phase timestamps (tools/trace_lik.py); p.trace is NULL in production
+#define BGH_TRACE(slot)                                                                          \
+    do {                                                                                         \
+        if (p.trace != nullptr && lane == 0)                                                     \
+            p.trace[((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * kLikWarps + warp) * 8 + (slot)] = global_timer_ns(); \
+    } while (0)
+
 template <int CL, int CPL>
 __global__ void __launch_bounds__(kLikThreads, 1) lik_kernel(const LikParams p)
 {
     constexpr int SL = 32 / CL;     // groups per warp
     constexpr int CH = 4 * CL;      // SNPs per group per chunk (SL * CH == kChunk)
     constexpr int CG = CL * CPL;    // chains per chain block
+    constexpr int B = kLikBatch;    // SNPs per branch-free batch
     static_assert(SL * CH == kChunk, "chunk geometry");
+    static_assert(CH % B == 0, "batch must divide the chunk");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SnpA* const smA_all = reinterpret_cast<SnpA*>(smem_raw);
-    SnpB* const smB_all = reinterpret_cast<SnpB*>(smem_raw + (size_t)kLikWarps * kChunk * sizeof(SnpA));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -110,16 +129,49 @@ __global__ void __launch_bounds__(kLikThreads, 1) lik_kernel(const LikParams p)
     const int v = (blockIdx.x * kLikWarps + warp) * SL + grp;
     const int Cp = p.Cp;
     const int ch0 = blockIdx.y * CG + lc;   // chain of slot k is ch0 + k*CL
+    const bool gene_model = p.model == BGH_MODEL_GENE_NORMAL;
 
-    SnpA* const smA = smA_all + warp * kChunk;
-    SnpB* const smB = smB_all + warp * kChunk;
+    // SNP i (0 <= i < CH) of this group lives at index i of the group's slice of each array
+    double* const sm_s = reinterpret_cast<double*>(smem_raw + (size_t)warp * kWarpStageBytes) + grp * (CH + 2);
+    double* const sm_nl = sm_s + kStride;
+    double* const sm_w = sm_nl + kStride;
+    int* const sm_g = reinterpret_cast<int*>(reinterpret_cast<double*>(smem_raw + (size_t)warp * kWarpStageBytes) + 3 * kStride) + grp * (CH + 4);
+    BGH_TRACE(0);
+    if (p.trace != nullptr && lane == 0)
+        p.trace[((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * kLikWarps + warp) * 8 + 7] = sm_id();
+
+    // ---- group descriptor, then get the first loads in flight before the exp() preamble --------
+    const int4 desc = p.groups[v];
+    const int ra = desc.x, rb = desc.y, flags = desc.z, g_first = desc.w;
+    const bool exclusive = (flags & kExclusive) != 0;
+    const bool active = ra < rb;
+    const double* const beta = p.q + (size_t)3 * Cp + ch0;   // gene model rows 3.. (this lane's chains)
+
+    int base = ra & ~(CH - 1);   // CH aligned so every lane's 4-vector is 16-byte aligned
+    float4 rs = make_float4(0.f, 0.f, 0.f, 0.f), rl = make_float4(1.f, 1.f, 1.f, 1.f);
+    int4 rg = make_int4(0, 0, 0, 0);
+    double braw[CPL], bn[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) braw[k] = bn[k] = 0.0;
+    if (active) {
+        rs = ldg_stream_f4(p.chi2 + base + lc * 4);
+        rl = ldg_stream_f4(p.ld + base + lc * 4);
+        rg = ldg_stream_i4(p.gid + base + lc * 4);
+        if (gene_model) {
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                braw[k] = beta[(size_t)g_first * Cp + k * CL];
+                bn[k] = (g_first + 1 < p.G) ? beta[(size_t)(g_first + 1) * Cp + k * CL] : 0.0;
+            }
+        }
+    }
 
     // ---- per-chain constants ----------------------------------------------------------------
     double e[CPL], mi[CPL], iW2[CPL];
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
         const int ch = ch0 + k * CL;
-        if (p.model == BGH_MODEL_GENE_NORMAL) {
+        if (gene_model) {
             const double xW = p.q[0 * Cp + ch];
             const double ev = p.q[1 * Cp + ch];
             const double xm = p.q[2 * Cp + ch];
@@ -132,99 +184,128 @@ __global__ void __launch_bounds__(kLikThreads, 1) lik_kernel(const LikParams p)
             iW2[k] = 0.0;
             mi[k] = sigmoid_d(xm);
             e[k] = p.fix ? (kGwFixLo + (kGwFixHi - kGwFixLo) * sigmoid_d(x0)) : x0;
+            braw[k] = bn[k] = mi[k];                 // the single slope of heritability.py:50-55
         }
     }
 
-    double b[CPL], db[CPL], bn[CPL];
-    double ag[CPL], ae[CPL], al[CPL], s1[CPL], s2[CPL];
+    if (blockIdx.x == 0 && warp == 0 && grp == 0) {   // hand the per-chain constants to finalize
 #pragma unroll
-    for (int k = 0; k < CPL; ++k) {
-        b[k] = db[k] = bn[k] = 0.0;
-        ag[k] = ae[k] = al[k] = s1[k] = s2[k] = 0.0;
+        for (int k = 0; k < CPL; ++k) {
+            p.cc[0 * Cp + ch0 + k * CL] = iW2[k];
+            p.cc[1 * Cp + ch0 + k * CL] = mi[k];
+        }
     }
 
-    const int4 desc = p.groups[v];
-    const int ra = desc.x, rb = desc.y, flags = desc.z;
+    double b[CPL], db[CPL];
+    double ag[CPL], ae[CPL], al[CPL], s1[CPL], s2[CPL], ax[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+        b[k] = p.c * braw[k];
+        db[k] = braw[k] - mi[k];
+        ag[k] = ae[k] = al[k] = s1[k] = s2[k] = ax[k] = 0.0;
+    }
 
-    if (ra < rb) {
+    BGH_TRACE(1);
+    if (active) {
         const bool head_partial = (flags & kHeadPartial) != 0;
         const bool tail_partial = (flags & kTailPartial) != 0;
-        const double* const beta = p.q + (size_t)3 * Cp;   // gene model rows 3..
-        const int g_first = __ldg(p.gid + ra);
         int cur = g_first;
 
         auto load_beta = [&](int g, double (&dst)[CPL]) {
 #pragma unroll
             for (int k = 0; k < CPL; ++k) {
-                if (p.model == BGH_MODEL_GENE_NORMAL)
-                    dst[k] = (g < p.G) ? beta[(size_t)g * Cp + ch0 + k * CL] : 0.0;
+                if (gene_model)
+                    dst[k] = (g < p.G) ? beta[(size_t)g * Cp + k * CL] : 0.0;
                 else
                     dst[k] = mi[k];
             }
         };
-        auto set_beta = [&](const double (&src)[CPL]) {
-#pragma unroll
-            for (int k = 0; k < CPL; ++k) {
-                b[k] = p.c * src[k];
-                db[k] = src[k] - mi[k];
-            }
-        };
         // gene `cur` is complete within this range (or the range ends): emit its sum
         auto flush = [&](bool final_flush) {
-            const bool to_head = (cur == g_first) && head_partial;
-            const bool to_tail = !to_head && final_flush && tail_partial;
-            if (to_head || to_tail) {
-                double* dst = p.slots + (size_t)(to_head ? v : p.NG + v) * Cp;
+            bool owner;
+            if (exclusive) {
+                // every group of this CTA accumulates the same gene: reduced in the CTA epilogue
 #pragma unroll
-                for (int k = 0; k < CPL; ++k) dst[ch0 + k * CL] = ag[k];
-            } else if (p.model == BGH_MODEL_GENE_NORMAL) {
-                double* dst = p.grad + (size_t)(3 + cur) * Cp;
+                for (int k = 0; k < CPL; ++k) ax[k] = ag[k];
+                owner = (flags & kOwner) != 0;
+            } else {
+                const bool to_head = (cur == g_first) && head_partial;
+                const bool to_tail = !to_head && final_flush && tail_partial;
+                if (to_head || to_tail) {
+                    double* dst = p.slots + (size_t)(to_head ? v : p.NG + v) * Cp + ch0;
 #pragma unroll
-                for (int k = 0; k < CPL; ++k) dst[ch0 + k * CL] = fma(p.c, ag[k], -db[k] * iW2[k]);
+                    for (int k = 0; k < CPL; ++k) dst[k * CL] = ag[k];
+                } else if (gene_model) {
+                    double* dst = p.grad + (size_t)(3 + cur) * Cp + ch0;
+#pragma unroll
+                    for (int k = 0; k < CPL; ++k) dst[k * CL] = fma(p.c, ag[k], -db[k] * iW2[k]);
+                }
+                owner = !to_head;   // this group holds the gene's first SNP: it owns the prior terms
             }
-            if (!to_head) {   // this group holds the gene's first SNP: it owns the prior terms
+            if (owner) {
 #pragma unroll
                 for (int k = 0; k < CPL; ++k) {
                     s1[k] += db[k];
                     s2[k] = fma(db[k], db[k], s2[k]);
                 }
             }
+        };
+        // switch to gene g (its raw beta in src), prefetch the row after it
+        auto enter_gene = [&](int g, const double (&src)[CPL]) {
 #pragma unroll
-            for (int k = 0; k < CPL; ++k) ag[k] = 0.0;
+            for (int k = 0; k < CPL; ++k) {
+                b[k] = p.c * src[k];
+                db[k] = src[k] - mi[k];
+            }
+            cur = g;
+            load_beta(g + 1, bn);   // genes are consecutive after the sort
+        };
+        auto accumulate = [&](const double sv, const double nlv, const double w) {
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                const double d = sv - e[k];
+                const double r = fma(nlv, b[k], d);
+                ag[k] += r;
+                const double t = r * w;
+                ae[k] += t;
+                al[k] = fma(r, t, al[k]);
+            }
+        };
+        // one SNP with the gene-boundary check (tail of a chunk / several boundaries in a batch)
+        auto step_checked = [&](int i) {
+            const int g_i = sm_g[i];
+            if (g_i != cur) {
+                flush(false);
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) ag[k] = 0.0;
+                if (g_i == cur + 1) {
+                    double tmp[CPL];
+#pragma unroll
+                    for (int k = 0; k < CPL; ++k) tmp[k] = bn[k];
+                    enter_gene(g_i, tmp);
+                } else {
+                    double tmp[CPL];
+                    load_beta(g_i, tmp);
+                    enter_gene(g_i, tmp);
+                }
+            }
+            accumulate(sm_s[i], sm_nl[i], sm_w[i]);
         };
 
-        {
-            double tmp[CPL];
-            load_beta(cur, tmp);
-            set_beta(tmp);
-            load_beta(cur + 1, bn);
-        }
-
-        // chunk loop; `base` is CH aligned so every lane's 4-vector is 16-byte aligned
-        int base = ra & ~(CH - 1);
-        float4 rs = ldg_stream_f4(p.chi2 + base + lc * 4);
-        float4 rl = ldg_stream_f4(p.ld + base + lc * 4);
-        int4 rg = ldg_stream_i4(p.gid + base + lc * 4);
         for (; base < rb; base += CH) {
-            // convert + stage: SNP i of this group lives at index i*SL + grp
+            // convert + stage: this lane's 4 consecutive SNPs -> 2 x STS.128 per fp64 array
             {
-                const float sv[4] = {rs.x, rs.y, rs.z, rs.w};
-                const float lv[4] = {rl.x, rl.y, rl.z, rl.w};
-                const int gv[4] = {rg.x, rg.y, rg.z, rg.w};
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int idx = (lc * 4 + t) * SL + grp;
-                    const double l = (double)lv[t];
-                    SnpA a;
-                    a.s = (double)sv[t];
-                    a.nl = -l;
-                    SnpB bb;
-                    bb.w = 1.0 / l;
-                    bb.g = gv[t];
-                    bb.pad = 0;
-                    smA[idx] = a;
-                    smB[idx] = bb;
-                }
+                const double l0 = (double)rl.x, l1 = (double)rl.y, l2 = (double)rl.z, l3 = (double)rl.w;
+                double2* const ps = reinterpret_cast<double2*>(sm_s + lc * 4);
+                double2* const pn = reinterpret_cast<double2*>(sm_nl + lc * 4);
+                double2* const pw = reinterpret_cast<double2*>(sm_w + lc * 4);
+                ps[0] = make_double2((double)rs.x, (double)rs.y);
+                ps[1] = make_double2((double)rs.z, (double)rs.w);
+                pn[0] = make_double2(-l0, -l1);
+                pn[1] = make_double2(-l2, -l3);
+                pw[0] = make_double2(__drcp_rn(l0), __drcp_rn(l1));
+                pw[1] = make_double2(__drcp_rn(l2), __drcp_rn(l3));
+                *reinterpret_cast<int4*>(sm_g + lc * 4) = rg;
             }
             __syncwarp(gmask);
             if (base + CH < rb) {
@@ -232,40 +313,84 @@ __global__ void __launch_bounds__(kLikThreads, 1) lik_kernel(const LikParams p)
                 rl = ldg_stream_f4(p.ld + base + CH + lc * 4);
                 rg = ldg_stream_i4(p.gid + base + CH + lc * 4);
             }
-            const int i0 = max(ra - base, 0);
+            int i = max(ra - base, 0);
             const int i1 = min(rb - base, CH);
-#pragma unroll 4
-            for (int i = i0; i < i1; ++i) {
-                const SnpA a = smA[i * SL + grp];
-                const SnpB bb = smB[i * SL + grp];
-                if (bb.g != cur) {
-                    flush(false);
-                    if (bb.g == cur + 1) {
-                        set_beta(bn);
-                    } else {
-                        double tmp[CPL];
-                        load_beta(bb.g, tmp);
-                        set_beta(tmp);
-                    }
-                    cur = bb.g;
-                    load_beta(cur + 1, bn);   // prefetch: genes are consecutive after the sort
-                }
+            // batches are B aligned (vector LDS); a range that starts mid-batch steps up to the boundary
+            for (; i < i1 && (i & (B - 1)) != 0; ++i) step_checked(i);
+            while (i + B <= i1) {
+                // SNPs are gene sorted: if the last SNP of the batch is still in `cur`, all of it is
+                const int g_last = sm_g[i + B - 1];
+                if (g_last == cur) {
+                    double2 s2v[B / 2], n2v[B / 2], w2v[B / 2];
 #pragma unroll
-                for (int k = 0; k < CPL; ++k) {
-                    const double d = a.s - e[k];
-                    const double r = fma(a.nl, b[k], d);
-                    ag[k] += r;
-                    const double t = r * bb.w;
-                    ae[k] += t;
-                    al[k] = fma(r, t, al[k]);
+                    for (int t = 0; t < B / 2; ++t) {
+                        s2v[t] = *reinterpret_cast<const double2*>(sm_s + i + 2 * t);
+                        n2v[t] = *reinterpret_cast<const double2*>(sm_nl + i + 2 * t);
+                        w2v[t] = *reinterpret_cast<const double2*>(sm_w + i + 2 * t);
+                    }
+#pragma unroll
+                    for (int t = 0; t < B / 2; ++t) {
+                        accumulate(s2v[t].x, n2v[t].x, w2v[t].x);
+                        accumulate(s2v[t].y, n2v[t].y, w2v[t].y);
+                    }
+                    i += B;
+                    continue;
+                }
+                // at least one gene boundary inside the batch: nlead SNPs still belong to `cur`
+                int nlead = 0;
+#pragma unroll
+                for (int t = 0; t < B - 1; ++t) nlead += (sm_g[i + t] == cur) ? 1 : 0;
+                if (sm_g[i + nlead] == g_last) {
+                    // exactly one boundary: [0,nlead) -> cur, [nlead,B) -> g_last. The two per-chain
+                    // sums that do not depend on the gene (ae, al) run straight through; only the
+                    // slope and the per-gene accumulator are selected per SNP.
+                    double raw2[CPL], b2[CPL], ag2[CPL];
+                    if (g_last == cur + 1) {
+#pragma unroll
+                        for (int k = 0; k < CPL; ++k) raw2[k] = bn[k];
+                    } else {
+                        load_beta(g_last, raw2);
+                    }
+#pragma unroll
+                    for (int k = 0; k < CPL; ++k) {
+                        b2[k] = p.c * raw2[k];
+                        ag2[k] = 0.0;
+                    }
+#pragma unroll
+                    for (int t = 0; t < B; ++t) {
+                        const double sv = sm_s[i + t], nlv = sm_nl[i + t];
+                        const double w = sm_w[i + t];
+                        const bool lead = t < nlead;
+#pragma unroll
+                        for (int k = 0; k < CPL; ++k) {
+                            const double d = sv - e[k];
+                            const double r = fma(nlv, lead ? b[k] : b2[k], d);
+                            if (lead) ag[k] += r; else ag2[k] += r;
+                            const double tt = r * w;
+                            ae[k] += tt;
+                            al[k] = fma(r, tt, al[k]);
+                        }
+                    }
+                    flush(false);
+#pragma unroll
+                    for (int k = 0; k < CPL; ++k) ag[k] = ag2[k];
+                    enter_gene(g_last, raw2);
+                    i += B;
+                } else {
+                    // several boundaries (genes shorter than a batch): step through the whole batch so
+                    // that the next one stays B aligned
+                    for (int t = 0; t < B; ++t) step_checked(i + t);
+                    i += B;
                 }
             }
+            for (; i < i1; ++i) step_checked(i);
             __syncwarp(gmask);
         }
         flush(true);
     }
 
-    // ---- CTA reduction of the four per-chain scalars (fixed order -> deterministic) ----------
+    BGH_TRACE(2);
+    // ---- CTA reduction of the per-chain scalars (fixed order -> deterministic) ---------------
     // 1) across the SL groups of a warp (same lc): xor-shuffle tree
 #pragma unroll
     for (int o = CL; o < 32; o <<= 1) {
@@ -275,29 +400,38 @@ __global__ void __launch_bounds__(kLikThreads, 1) lik_kernel(const LikParams p)
             ae[k] += __shfl_xor_sync(0xffffffffu, ae[k], o);
             s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], o);
             s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], o);
+            ax[k] += __shfl_xor_sync(0xffffffffu, ax[k], o);
         }
     }
     // 2) across warps through shared memory (reuses the staging area)
     __syncthreads();
-    double* const red = reinterpret_cast<double*>(smem_raw);   // [kLikWarps][4][CG]
+    BGH_TRACE(3);
+    double* const red = reinterpret_cast<double*>(smem_raw);   // [kLikWarps][5][CG]
     if (grp == 0) {
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
             const int cc = lc + k * CL;
-            red[(warp * 4 + 0) * CG + cc] = al[k];
-            red[(warp * 4 + 1) * CG + cc] = ae[k];
-            red[(warp * 4 + 2) * CG + cc] = s1[k];
-            red[(warp * 4 + 3) * CG + cc] = s2[k];
+            red[(warp * 5 + 0) * CG + cc] = al[k];
+            red[(warp * 5 + 1) * CG + cc] = ae[k];
+            red[(warp * 5 + 2) * CG + cc] = s1[k];
+            red[(warp * 5 + 3) * CG + cc] = s2[k];
+            red[(warp * 5 + 4) * CG + cc] = ax[k];
         }
     }
     __syncthreads();
-    for (int o = threadIdx.x; o < 4 * CG; o += blockDim.x) {
+    const bool cta_exclusive = (p.groups[blockIdx.x * kLikWarps * SL].z & kExclusive) != 0;
+    for (int o = threadIdx.x; o < 5 * CG; o += blockDim.x) {
+        const int which = o / CG, cc = o % CG;
+        if (which == 4 && !cta_exclusive) continue;
         double acc = 0.0;
 #pragma unroll
-        for (int w = 0; w < kLikWarps; ++w) acc += red[w * 4 * CG + o];
-        const int which = o / CG, cc = o % CG;
-        p.part[((size_t)blockIdx.x * 4 + which) * Cp + blockIdx.y * CG + cc] = acc;
+        for (int w = 0; w < kLikWarps; ++w) acc += red[w * 5 * CG + o];
+        if (which < 4)
+            p.part[((size_t)blockIdx.x * 4 + which) * Cp + blockIdx.y * CG + cc] = acc;
+        else
+            p.slots[((size_t)2 * p.NG + blockIdx.x) * Cp + blockIdx.y * CG + cc] = acc;
     }
+    BGH_TRACE(4);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -307,59 +441,105 @@ __global__ void __launch_bounds__(kLikThreads, 1) lik_kernel(const LikParams p)
 struct ChainSums {
     double A_ll, A_e, S1, S2;
 };
+// Sum-independent per-chain terms of the closing formulas: computed once per evaluation, in
+// parallel with the partial-sum reduction (finalize) or directly (finish kernel).
+//   gene model: {iW, iW2, mi, lp0}   lp0 = all logp terms that do not involve the four sums
+//   gw model  : {sg0 (sigmoid of x0 when the intercept is "fixed"), -, mi, lp0}
+struct ChainConst {
+    double iW, iW2, mi, lp0;
+};
 
-__device__ void finish_chain(const FinParams& p, int ch, const ChainSums& s)
+__device__ ChainConst chain_const(const FinParams& p, int ch)
+{
+    const int Cp = p.Cp;
+    ChainConst c;
+    if (p.model == BGH_MODEL_GENE_NORMAL) {
+        const double xW = p.q[0 * Cp + ch], e = p.q[1 * Cp + ch], xm = p.q[2 * Cp + ch];
+        const double ax = fabs(xm);
+        const double u = exp(-ax);                 // one exp + one log1p serve sigmoid and both logs
+        const double L = log1p(u);
+        c.iW = exp(-xW);
+        c.iW2 = c.iW * c.iW;
+        c.mi = (xm >= 0.0 ? 1.0 : u) / (1.0 + u);
+        const double G = (double)p.G_total;
+        // log sigmoid(x) + log(1 - sigmoid(x)) = -|x| - 2 log1p(exp(-|x|))
+        double lp = (-c.iW - 2.0 * xW) + xW;                       // InverseGamma(1,1) + log-Jacobian
+        lp += -0.5 * (e - 1.0) * (e - 1.0) - 0.5 * kLog2Pi;        // Normal(1,1)
+        lp += -ax - 2.0 * L;                                       // Beta(1,1)=0 ; logodds Jacobian
+        lp += -G * xW - 0.5 * G * kLog2Pi;                         // Normal(beta | mi, W) constants
+        lp += p.lik_const;
+        c.lp0 = lp;
+    } else {
+        const double x0 = p.q[0 * Cp + ch], xm = p.q[1 * Cp + ch];
+        const double ax = fabs(xm);
+        const double u = exp(-ax);
+        const double L = log1p(u);
+        c.mi = (xm >= 0.0 ? 1.0 : u) / (1.0 + u);
+        const double l1m = (xm >= 0.0 ? -xm : 0.0) - L;            // log(1 - mi)
+        double lp = l1m + 0.69314718055994530942;                  // Beta(1,2)
+        lp += -ax - 2.0 * L;                                       // logodds Jacobian
+        c.iW = 0.0;
+        if (p.fix) {
+            // Uniform(lo,hi) logp = -log(hi-lo); interval Jacobian = log(hi-lo) + log sigmoid'(x0)
+            const double a0 = fabs(x0), u0 = exp(-a0);
+            c.iW = (x0 >= 0.0 ? 1.0 : u0) / (1.0 + u0);            // sigmoid(x0)
+            lp += -a0 - 2.0 * log1p(u0);
+        } else {
+            lp += -0.5 * (x0 - 1.0) * (x0 - 1.0) - 0.5 * kLog2Pi;
+        }
+        lp += p.lik_const;
+        c.iW2 = 0.0;
+        c.lp0 = lp;
+    }
+    return c;
+}
+
+__device__ __forceinline__ void finish_chain(const FinParams& p, int ch, const ChainSums& s, const ChainConst& c)
 {
     const int Cp = p.Cp;
     if (p.model == BGH_MODEL_GENE_NORMAL) {
-        const double xW = p.q[0 * Cp + ch], e = p.q[1 * Cp + ch], xm = p.q[2 * Cp + ch];
-        const double iW = exp(-xW), iW2 = exp(-2.0 * xW);
-        const double mi = sigmoid_d(xm);
+        const double e = p.q[1 * Cp + ch];
         const double G = (double)p.G_total;
-        double lp = (-iW - 2.0 * xW) + xW;                        // InverseGamma(1,1) + log-Jacobian
-        lp += -0.5 * (e - 1.0) * (e - 1.0) - 0.5 * kLog2Pi;       // Normal(1,1)
-        lp += log_sigmoid_d(xm) + log1m_sigmoid_d(xm);            // Beta(1,1)=0 ; logodds Jacobian
-        lp += -0.5 * s.S2 * iW2 - G * xW - 0.5 * G * kLog2Pi;     // Normal(beta | mi, W)
-        lp += -0.5 * s.A_ll + p.lik_const;                        // likelihood
-        p.logp[ch] = lp;
-        p.grad[0 * Cp + ch] = iW - 1.0 + s.S2 * iW2 - G;
+        p.logp[ch] = c.lp0 - 0.5 * s.S2 * c.iW2 - 0.5 * s.A_ll;
+        p.grad[0 * Cp + ch] = c.iW - 1.0 + s.S2 * c.iW2 - G;
         p.grad[1 * Cp + ch] = -(e - 1.0) + (p.fix ? 0.0 : s.A_e);
-        p.grad[2 * Cp + ch] = 1.0 - 2.0 * mi + mi * (1.0 - mi) * s.S1 * iW2;
+        p.grad[2 * Cp + ch] = 1.0 - 2.0 * c.mi + c.mi * (1.0 - c.mi) * s.S1 * c.iW2;
     } else {
-        const double x0 = p.q[0 * Cp + ch], xm = p.q[1 * Cp + ch];
-        double lp = 0.0, g0;
+        const double x0 = p.q[0 * Cp + ch];
+        p.logp[ch] = c.lp0 - 0.5 * s.A_ll;
         if (p.fix) {
-            // Uniform(lo,hi) logp = -log(hi-lo); interval Jacobian = log(hi-lo) + log sigmoid'(x0)
-            const double sg = sigmoid_d(x0);
-            lp += log_sigmoid_d(x0) + log1m_sigmoid_d(x0);
-            g0 = s.A_e * (kGwFixHi - kGwFixLo) * sg * (1.0 - sg) + (1.0 - 2.0 * sg);
+            const double sg = c.iW;
+            p.grad[0 * Cp + ch] = s.A_e * (kGwFixHi - kGwFixLo) * sg * (1.0 - sg) + (1.0 - 2.0 * sg);
         } else {
-            lp += -0.5 * (x0 - 1.0) * (x0 - 1.0) - 0.5 * kLog2Pi;
-            g0 = -(x0 - 1.0) + s.A_e;
+            p.grad[0 * Cp + ch] = -(x0 - 1.0) + s.A_e;
         }
-        lp += log1m_sigmoid_d(xm) + 0.69314718055994530942;       // Beta(1,2)
-        lp += log_sigmoid_d(xm) + log1m_sigmoid_d(xm);            // logodds Jacobian
-        lp += -0.5 * s.A_ll + p.lik_const;
-        p.logp[ch] = lp;
-        p.grad[0 * Cp + ch] = g0;
     }
 }
 
-// gradient row of a gene from its total residual sum
-__device__ __forceinline__ void finish_gene(const FinParams& p, int gene, int ch, double sum_r)
+// gradient row of a gene from its total residual sum.  The per-chain constants (1/W^2, mi) were
+// computed by the likelihood kernel and left in p.cc, so no exp() chain sits on this path.
+struct GeneCoef {
+    double iW2, mi, beta;
+};
+__device__ __forceinline__ GeneCoef load_gene_coef(const FinParams& p, int gene, int ch, bool needed)
+{
+    GeneCoef gc;
+    gc.iW2 = gc.mi = gc.beta = 0.0;
+    if (needed) {
+        gc.iW2 = p.cc[0 * p.Cp + ch];
+        gc.mi = p.cc[1 * p.Cp + ch];
+        if (p.model == BGH_MODEL_GENE_NORMAL) gc.beta = p.q[(size_t)(3 + gene) * p.Cp + ch];
+    }
+    return gc;
+}
+__device__ __forceinline__ void finish_gene(const FinParams& p, int gene, int ch, double sum_r, const GeneCoef& gc)
 {
     const int Cp = p.Cp;
     if (p.model == BGH_MODEL_GENE_NORMAL) {
-        const double xW = p.q[0 * Cp + ch], xm = p.q[2 * Cp + ch];
-        const double iW2 = exp(-2.0 * xW);
-        const double mi = sigmoid_d(xm);
-        const double bta = p.q[(size_t)(3 + gene) * Cp + ch];
-        p.grad[(size_t)(3 + gene) * Cp + ch] = fma(p.c, sum_r, -(bta - mi) * iW2);
+        p.grad[(size_t)(3 + gene) * Cp + ch] = fma(p.c, sum_r, -(gc.beta - gc.mi) * gc.iW2);
     } else {
-        const double xm = p.q[1 * Cp + ch];
-        const double mi = sigmoid_d(xm);
         // (c*sum_r - 1/(1-mi)) * mi(1-mi) + (1 - 2mi)
-        p.grad[1 * Cp + ch] = p.c * sum_r * mi * (1.0 - mi) + 1.0 - 3.0 * mi;
+        p.grad[1 * Cp + ch] = p.c * sum_r * gc.mi * (1.0 - gc.mi) + 1.0 - 3.0 * gc.mi;
     }
 }
 
@@ -371,87 +551,113 @@ __device__ __forceinline__ void finish_gene(const FinParams& p, int gene, int ch
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinParams p)
 {
-    __shared__ double sm[32][33];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ double sm[32 * 33];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Cp = p.Cp;
 
     if (blockIdx.x == 0) {
+        // ---- per-CTA scalar partials [n_cta][4][Cp] -> payload rows 0..3 (all loads independent),
+        // while the last 4 warps evaluate the sum-independent transcendental terms of each chain.
+        __shared__ double cst[4][kFinConstChains];
         const int n_out = 4 * Cp;
-        const int nob = (n_out + 31) / 32;                 // output blocks of 32
-        const int wpb = nob >= 32 ? 1 : 32 / nob;          // warps cooperating per block
-        for (int ob0 = 0; ob0 < nob; ob0 += 32 / wpb) {
-            const int ob = ob0 + warp / wpb;
-            const int sub = warp % wpb;
-            const int o = ob * 32 + lane;
-            double acc = 0.0;
-            if (ob < nob && o < n_out) {
-#pragma unroll 4
-                for (int cta = sub; cta < p.n_cta; cta += wpb) acc += p.part[(size_t)cta * n_out + o];
+        constexpr int kSumThreads = kFinThreads - 128;
+        for (int c0 = 0; c0 < Cp; c0 += kFinConstChains) {
+            const int nc = min(kFinConstChains, Cp - c0);      // chains in this pass
+            if (tid >= kSumThreads) {
+                if (p.finish_inline) {
+                    for (int cc = tid - kSumThreads; cc < nc; cc += 128) {
+                        const ChainConst k = chain_const(p, c0 + cc);
+                        cst[0][cc] = k.iW; cst[1][cc] = k.iW2; cst[2][cc] = k.mi; cst[3][cc] = k.lp0;
+                    }
+                }
+            } else {
+                // outputs of this pass: the 4 rows x nc chains; R row groups of nb threads each
+                const int nb = 4 * nc;                          // <= 512
+                const int R = kSumThreads / nb;
+                const int oo = tid % nb, sub = tid / nb;
+                const int o = (oo / nc) * Cp + c0 + (oo % nc);  // index inside a [4][Cp] row
+                double acc = 0.0;
+                if (sub < R) {
+#pragma unroll 8
+                    for (int row = sub; row < p.n_cta; row += R) acc += p.part[(size_t)row * n_out + o];
+                }
+                sm[tid] = acc;
             }
-            sm[warp][lane] = acc;
             __syncthreads();
-            if (sub == 0 && ob < nob && o < n_out) {
+            if (tid < 4 * nc) {
+                const int nb = 4 * nc, R = kSumThreads / nb;
                 double tot = 0.0;
-                for (int w = 0; w < wpb; ++w) tot += sm[warp + w][lane];
-                p.payload[o] = tot;   // rows 0..3 of the payload are [4][Cp]
+                for (int r = 0; r < R; ++r) tot += sm[r * nb + tid];
+                sm[tid] = tot;
+                p.payload[(tid / nc) * Cp + c0 + (tid % nc)] = tot;   // rows 0..3 of the payload are [4][Cp]
             }
             __syncthreads();
-        }
-        if (p.finish_inline) {
-            __threadfence_block();
-            __syncthreads();
-            for (int ch = threadIdx.x; ch < Cp; ch += blockDim.x) {
-                ChainSums s;
-                s.A_ll = p.payload[0 * Cp + ch];
-                s.A_e = p.payload[1 * Cp + ch];
-                s.S1 = p.payload[2 * Cp + ch];
-                s.S2 = p.payload[3 * Cp + ch];
-                finish_chain(p, ch, s);
+            if (p.finish_inline && tid < nc) {
+                ChainSums cs;
+                cs.A_ll = sm[0 * nc + tid];
+                cs.A_e = sm[1 * nc + tid];
+                cs.S1 = sm[2 * nc + tid];
+                cs.S2 = sm[3 * nc + tid];
+                ChainConst k;
+                k.iW = cst[0][tid]; k.iW2 = cst[1][tid]; k.mi = cst[2][tid]; k.lp0 = cst[3][tid];
+                finish_chain(p, c0 + tid, cs, k);
             }
+            __syncthreads();
         }
         return;
     }
 
     if ((int)blockIdx.x > p.n_long) {
-        // short lists (<= kShortSplit slots): one warp per split gene, lanes = chains
-        const int k = p.n_long + ((int)blockIdx.x - 1 - p.n_long) * 32 + warp;
+        // ---- short lists (<= 32 slots): one warp per (split gene, block of 32 chains)
+        const int ncb = (Cp + 31) / 32;
+        const int task = ((int)blockIdx.x - 1 - p.n_long) * 32 + warp;
+        const int k = p.n_long + task / ncb, cb = task % ncb;
         if (k >= p.n_split) return;
-        const int s0 = p.split_ptr[k], s1 = p.split_ptr[k + 1];
+        const int s0 = p.split_ptr[k], n = p.split_ptr[k + 1] - s0;
         const int gene = p.split_gene[k], row = p.split_row[k];
-        for (int cb = 0; cb < Cp; cb += 32) {
-            const int ch = cb + lane;
-            if (ch >= Cp) break;
-            double tot = 0.0;
-            for (int i = s0; i < s1; ++i) tot += p.slots[(size_t)p.split_slots[i] * Cp + ch];
+        const int ch = cb * 32 + lane;
+        const bool on = ch < Cp;
+        const int my_slot = (lane < n) ? p.split_slots[s0 + lane] : 0;
+        GeneCoef gc = load_gene_coef(p, gene, on ? ch : 0, row < 0);
+        double tot = 0.0;
+#pragma unroll 4
+        for (int i = 0; i < n; ++i) {
+            const int slot = __shfl_sync(0xffffffffu, my_slot, i);
+            if (on) tot += p.slots[(size_t)slot * Cp + ch];
+        }
+        if (on) {
             if (row >= 0)
-                p.payload[(size_t)(4 + row) * Cp + ch] = tot;
+                p.payload[(size_t)(4 + row) * Cp + ch] = tot;   // rank-shared: finished after all-reduce
             else
-                finish_gene(p, gene, ch, tot);
+                finish_gene(p, gene, ch, tot, gc);
         }
         return;
     }
 
-    // long lists: one CTA per split gene, warp w takes slots w, w+32, ...; fixed-order combine
+    // ---- long lists: one CTA per split gene, warp w takes slots w, w+32, ...; fixed-order combine
     const int k = blockIdx.x - 1;
     const int s0 = p.split_ptr[k], s1 = p.split_ptr[k + 1];
     const int gene = p.split_gene[k], row = p.split_row[k];
     for (int cb = 0; cb < Cp; cb += 32) {
         const int ch = cb + lane;
+        const bool on = ch < Cp;
+        GeneCoef gc = load_gene_coef(p, gene, on ? ch : 0, row < 0 && warp == 0);
         double acc = 0.0;
-        if (ch < Cp) {
 #pragma unroll 4
-            for (int i = s0 + warp; i < s1; i += 32) acc += p.slots[(size_t)p.split_slots[i] * Cp + ch];
+        for (int i = s0 + warp; i < s1; i += 32) {
+            const int slot = p.split_slots[i];
+            if (on) acc += p.slots[(size_t)slot * Cp + ch];
         }
-        sm[warp][lane] = acc;
+        sm[warp * 33 + lane] = acc;
         __syncthreads();
-        if (warp == 0 && ch < Cp) {
+        if (warp == 0 && on) {
             double tot = 0.0;
 #pragma unroll
-            for (int w = 0; w < 32; ++w) tot += sm[w][lane];
+            for (int w = 0; w < 32; ++w) tot += sm[w * 33 + lane];
             if (row >= 0)
-                p.payload[(size_t)(4 + row) * Cp + ch] = tot;   // rank-shared: finished after all-reduce
+                p.payload[(size_t)(4 + row) * Cp + ch] = tot;
             else
-                finish_gene(p, gene, ch, tot);
+                finish_gene(p, gene, ch, tot, gc);
         }
         __syncthreads();
     }
@@ -468,10 +674,12 @@ __global__ void finish_kernel(const FinParams p)
     s.A_e = p.payload[1 * Cp + ch];
     s.S1 = p.payload[2 * Cp + ch];
     s.S2 = p.payload[3 * Cp + ch];
-    finish_chain(p, ch, s);
-    if (p.first_gene_row >= 0) finish_gene(p, 0, ch, p.payload[(size_t)(4 + p.first_gene_row) * Cp + ch]);
+    finish_chain(p, ch, s, chain_const(p, ch));
+    if (p.first_gene_row >= 0)
+        finish_gene(p, 0, ch, p.payload[(size_t)(4 + p.first_gene_row) * Cp + ch], load_gene_coef(p, 0, ch, true));
     if (p.last_gene_row >= 0 && !(p.G_local == 1 && p.first_gene_row >= 0))
-        finish_gene(p, p.G_local - 1, ch, p.payload[(size_t)(4 + p.last_gene_row) * Cp + ch]);
+        finish_gene(p, p.G_local - 1, ch, p.payload[(size_t)(4 + p.last_gene_row) * Cp + ch],
+                    load_gene_coef(p, p.G_local - 1, ch, true));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -566,8 +774,8 @@ cudaError_t launch_lik(const LikParams& p, int CL, int CPL, int n_cta, int chain
 
 cudaError_t launch_finalize(const FinParams& p, cudaStream_t s)
 {
-    const int n_short = p.n_split - p.n_long;
-    finalize_kernel<<<1 + p.n_long + (n_short + 31) / 32, kFinThreads, 0, s>>>(p);
+    const int n_tasks = (p.n_split - p.n_long) * ((p.Cp + 31) / 32);   // (short split gene, 32-chain block)
+    finalize_kernel<<<1 + p.n_long + (n_tasks + 31) / 32, kFinThreads, 0, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,71 @@
+// Internal declarations of the batched NUTS kernels (bgh_sampler.cu) used by bgh_api.cu.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "baghera_b200.h"
+
+namespace bgh {
+
+constexpr int kNutsMaxDepth = BGH_NUTS_MAX_DEPTH;
+constexpr int kNutsMaxPartials = 1 + 2 * kNutsMaxDepth;
+
+// vector slots of the state tensor [n_slots][D][Cp] (public numbering: include/baghera_b200.h)
+enum : int {
+    kSlotQP = BGH_NUTS_SLOT_Q, kSlotGP = BGH_NUTS_SLOT_GRAD, kSlotVar = BGH_NUTS_SLOT_VAR,
+    kSlotQL = 3, kSlotPL, kSlotGL, kSlotQR, kSlotPR, kSlotGR, kSlotQW, kSlotPW, kSlotGW, kSlotQS, kSlotGS,
+    kSlotPSumTree, kSlotPSumRun,
+    kSlotFgMean = BGH_NUTS_SLOT_FG_MEAN, kSlotFgRaw = BGH_NUTS_SLOT_FG_RAW,
+    kSlotBgMean = BGH_NUTS_SLOT_BG_MEAN, kSlotBgRaw = BGH_NUTS_SLOT_BG_RAW,
+    kSlotCount = BGH_NUTS_N_SLOTS
+};
+static_assert(kSlotPSumRun + 1 == kSlotFgMean, "slot numbering");
+static_assert(kSlotBgRaw + 1 == kSlotCount, "slot numbering");
+
+// per-chain scalars sc[k][Cp]
+enum : int {
+    kScEps = BGH_NUTS_SC_EPS, kScLogpProp = BGH_NUTS_SC_LOGP, kScEnergyProp, kScE0, kScLogSizeTree, kScLogSizeSub,
+    kScLogpSub, kScEnergySub, kScAcceptSum, kScNProp, kScMaxDE,
+    kScDaLogStep, kScDaLogBar, kScDaHbar, kScDaCount, kScDaMu,
+    kScCount = BGH_NUTS_N_SC
+};
+static_assert(kScDaMu + 1 == kScCount, "scalar numbering");
+
+// per-chain flags fl[k][Cp]
+enum : int {
+    kFlDir = 0, kFlActive, kFlDone, kFlSubValid, kFlTake, kFlTakeTop, kFlMerge, kFlDepth, kFlDiverging, kFlTurning,
+    kFlBadStart,
+    kFlCount = BGH_NUTS_N_FL
+};
+static_assert(kFlBadStart + 1 == kFlCount, "flag numbering");
+
+struct NutsParams {
+    double* state;      // [kSlotCount][D][Cp]
+    double* ckpt;       // [2][kNutsMaxDepth][D][Cp]   {p, running p_sum} at the even leaves
+    double* sc;         // [kScCount][Cp]
+    int* fl;            // [kFlCount][Cp]
+    double* partials;   // [n_vec_blocks][kNutsMaxPartials][Cp]
+    double* sums;       // [kNutsMaxPartials][Cp]
+    const double* logp_w;   // [Cp] logp at the working position (written by the likelihood path)
+    int* n_active;      // device scalar
+    int D, Cp, C;
+    int n_vec_blocks;
+    int coord_offset;   // global index of local coordinate 0 (sharded runs)
+    unsigned long long seed;
+    long long draw;
+    double emax, target_accept, da_gamma, da_kappa, da_t0;
+};
+
+cudaError_t nuts_launch_begin(const NutsParams& p, cudaStream_t s);
+cudaError_t nuts_launch_dir(const NutsParams& p, cudaStream_t s);
+cudaError_t nuts_launch_leap1(const NutsParams& p, int first, cudaStream_t s);
+cudaError_t nuts_launch_leap2(const NutsParams& p, int leaf, int store_level, int lvl_min, int lvl_max, cudaStream_t s);
+cudaError_t nuts_launch_end_doubling(const NutsParams& p, int max_depth, cudaStream_t s);
+cudaError_t nuts_launch_adapt_mass(const NutsParams& p, double fg_w, double bg_w, int switch_window, cudaStream_t s);
+cudaError_t nuts_launch_finish(const NutsParams& p, int tune, double* stats, cudaStream_t s);
+cudaError_t nuts_launch_stop_tuning(const NutsParams& p, cudaStream_t s);
+cudaError_t nuts_launch_init(const NutsParams& p, double step0, cudaStream_t s);
+constexpr int kNutsLaunchesPerLeaf = 3;   // leap1, leap2, leaf scalar (plus the likelihood + finalize)
+
+}  // namespace bgh

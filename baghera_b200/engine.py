@@ -164,12 +164,13 @@ class Engine:
         return v.value
 
 
-def debug_plan(gid_sorted, G, n_groups, first_partial=False, last_partial=False):
-    """Host-only work plan (no GPU): returns dict(off, flags, split_gene, split_ptr, split_slots)."""
+def debug_plan(gid_sorted, G, n_cta, groups_per_cta=16, first_partial=False, last_partial=False):
+    """Host-only work plan (no GPU): returns dict(off, flags, split_gene, split_ptr, split_slots, n_cta)."""
+    n_groups = n_cta * groups_per_cta
     L = _lib.lib()
     gid = np.ascontiguousarray(gid_sorted, dtype=np.int32)
     M = gid.shape[0]
-    cap = 2 * n_groups + 8
+    cap = 3 * n_groups + 8
     off = np.zeros(n_groups + 1, np.int32)
     flags = np.zeros(n_groups, np.int32)
     ns = ctypes.c_int32()
@@ -177,10 +178,10 @@ def debug_plan(gid_sorted, G, n_groups, first_partial=False, last_partial=False)
     sp = np.zeros(cap + 1, np.int32)
     ss = np.zeros(cap, np.int32)
     P = ctypes.POINTER(ctypes.c_int32)
-    rc = L.bgh_debug_plan(M, gid.ctypes.data_as(P), int(G), int(n_groups), int(first_partial), int(last_partial),
+    rc = L.bgh_debug_plan(M, gid.ctypes.data_as(P), int(G), int(n_cta), int(groups_per_cta), int(first_partial), int(last_partial),
                           off.ctypes.data_as(P), flags.ctypes.data_as(P), ctypes.byref(ns), sg.ctypes.data_as(P),
                           sp.ctypes.data_as(P), ss.ctypes.data_as(P), cap)
     check(rc)
     n = ns.value
-    return dict(off=off, flags=flags, split_gene=sg[:n].copy(), split_ptr=sp[:n + 1].copy(),
+    return dict(off=off, flags=flags, n_cta=n_cta, groups_per_cta=groups_per_cta, split_gene=sg[:n].copy(), split_ptr=sp[:n + 1].copy(),
                 split_slots=ss[:sp[n]].copy())

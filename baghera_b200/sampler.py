@@ -1,0 +1,184 @@
+"""PyTorch-hosted batched-chain NUTS driver (replaces ``pm.sample`` at
+ref: baghera_tool/gene_regression.py:100-106 and ref: baghera_tool/heritability.py:56-62).
+
+torch owns the memory and the stream; every arithmetic step of a transition (momentum refresh,
+leapfrog, likelihood + gradient, tree bookkeeping, accept / multinomial draws, adaptation) runs in
+libbaghera_b200.so (csrc/bgh_sampler.cu, csrc/bgh_lik.cu).  Semantics: PyMC3 3.6 NUTS with
+``init='jitter+adapt_diag'`` [recalled, SURVEY §8a] — one independent adaptation per chain, tuning
+draws discarded, ``early_max_treedepth=8`` for the first 200 tuning draws then ``max_treedepth=10``.
+"""
+from __future__ import annotations
+
+import ctypes
+import time
+
+import numpy as np
+
+from . import _lib
+from ._lib import (NUTS_MAX_DEPTH, NUTS_MAX_PARTIALS, NUTS_N_FL, NUTS_N_SC, NUTS_N_SLOTS, NUTS_N_STATS,
+                   NUTS_SC_EPS, NUTS_SC_LOGP, NUTS_SLOT_BG_MEAN, NUTS_SLOT_BG_RAW, NUTS_SLOT_FG_MEAN,
+                   NUTS_SLOT_FG_RAW, NUTS_SLOT_GRAD, NUTS_SLOT_Q, NUTS_SLOT_VAR, bgh_nuts_buffers, bgh_nuts_cfg,
+                   check)
+
+STAT_NAMES = ("depth", "mean_tree_accept", "tree_size", "diverging", "energy", "step_size", "model_logp",
+              "max_energy_error")
+ADAPT_WINDOW = 101          # quadpotential.QuadPotentialDiagAdapt(adaptation_window=101)
+INITIAL_WEIGHT = 10.0       # init_nuts('jitter+adapt_diag'): QuadPotentialDiagAdapt(ndim, mean, var, 10)
+EARLY_MAX_TREEDEPTH, MAX_TREEDEPTH, EARLY_DRAWS = 8, 10, 200
+
+
+class NutsSampler:
+    def __init__(self, engine, seed=20211, target_accept=0.90):
+        import torch
+
+        self.eng = engine
+        self.t = torch
+        self.L = engine.L
+        dev, f64 = engine.device, torch.float64
+        D, Cp = engine.D, engine.Cp
+        self.n_vec_blocks = int(self.L.bgh_nuts_vec_blocks(engine.ctx))
+        self.state = torch.zeros((NUTS_N_SLOTS, D, Cp), dtype=f64, device=dev)
+        self.ckpt = torch.zeros((2, NUTS_MAX_DEPTH, D, Cp), dtype=f64, device=dev)
+        self.sc = torch.zeros((NUTS_N_SC, Cp), dtype=f64, device=dev)
+        self.fl = torch.zeros((NUTS_N_FL, Cp), dtype=torch.int32, device=dev)
+        self.partials = torch.zeros((self.n_vec_blocks, NUTS_MAX_PARTIALS, Cp), dtype=f64, device=dev)
+        self.sums = torch.zeros((NUTS_MAX_PARTIALS, Cp), dtype=f64, device=dev)
+        self.logp_w = torch.zeros(Cp, dtype=f64, device=dev)
+        self.stats = torch.zeros((NUTS_N_STATS, Cp), dtype=f64, device=dev)
+        self.n_active_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.n_active_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        b = bgh_nuts_buffers()
+        for name in ("state", "ckpt", "sc", "fl", "partials", "sums", "logp_w", "stats"):
+            setattr(b, name, getattr(self, name).data_ptr())
+        b.n_active_dev = self.n_active_dev.data_ptr()
+        b.n_active_host = self.n_active_host.data_ptr()
+        self.buf = b
+        cfg = bgh_nuts_cfg()
+        self.L.bgh_nuts_cfg_default(ctypes.byref(cfg))
+        cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        cfg.target_accept = float(target_accept)
+        self.cfg = cfg
+        self.draw = 0
+        self.n_adapt = 0
+        self.fg_w, self.bg_w = INITIAL_WEIGHT, 0.0
+        self.total_leapfrogs = 0
+
+    # ------------------------------------------------------------------ views
+    @property
+    def q(self):
+        return self.state[NUTS_SLOT_Q]
+
+    @property
+    def var(self):
+        return self.state[NUTS_SLOT_VAR]
+
+    @property
+    def step_size(self):
+        return self.sc[NUTS_SC_EPS, :self.eng.C]
+
+    @property
+    def logp(self):
+        return self.sc[NUTS_SC_LOGP, :self.eng.C]
+
+    def _stream(self):
+        return ctypes.c_void_p(self.t.cuda.current_stream(self.eng.device).cuda_stream)
+
+    # ------------------------------------------------------------------ init='jitter+adapt_diag'
+    def init(self, q0_cd):
+        """q0_cd: float64[C, D] start points (test point + U(-1,1) jitter per chain)."""
+        t = self.t
+        q0 = np.asarray(q0_cd, dtype=np.float64)
+        self.state[NUTS_SLOT_Q].copy_(self.eng.to_device_layout(q0))
+        self.state[NUTS_SLOT_VAR].fill_(1.0)
+        mean = t.as_tensor(q0.mean(axis=0), dtype=t.float64, device=self.eng.device)
+        self.state[NUTS_SLOT_FG_MEAN].copy_(mean[:, None].expand(-1, self.eng.Cp))
+        self.state[NUTS_SLOT_FG_RAW].fill_(INITIAL_WEIGHT)          # raw_var = initial_diag * weight
+        self.state[NUTS_SLOT_BG_MEAN].zero_()
+        self.state[NUTS_SLOT_BG_RAW].zero_()
+        self.fg_w, self.bg_w, self.n_adapt, self.draw = INITIAL_WEIGHT, 0.0, 0, 0
+        check(self.L.bgh_nuts_init(self.eng.ctx, ctypes.byref(self.buf), ctypes.byref(self.cfg), self._stream()),
+              self.eng.ctx)
+        t.cuda.synchronize(self.eng.device)
+        lp = self.logp.cpu().numpy()
+        if not np.all(np.isfinite(lp)):
+            raise ValueError("Bad initial energy: logp is not finite at the start point of chains %s"
+                             % np.flatnonzero(~np.isfinite(lp)).tolist())
+
+    # ------------------------------------------------------------------ one transition
+    def transition(self, tune, max_treedepth=MAX_TREEDEPTH):
+        fg_w = bg_w = 0.0
+        switch = 0
+        if tune:
+            # quadpotential.QuadPotentialDiagAdapt.update: add the sample to both estimators, refresh
+            # the variance from the foreground one, switch windows every ADAPT_WINDOW samples
+            self.fg_w += 1.0
+            self.bg_w += 1.0
+            fg_w, bg_w = self.fg_w, self.bg_w
+            switch = int(self.n_adapt > 0 and self.n_adapt % ADAPT_WINDOW == 0)
+        n_leap = ctypes.c_int32(0)
+        check(self.L.bgh_nuts_transition(self.eng.ctx, ctypes.byref(self.buf), ctypes.byref(self.cfg), self.draw,
+                                         int(bool(tune)), int(max_treedepth), fg_w, bg_w, switch, self._stream(),
+                                         ctypes.byref(n_leap)), self.eng.ctx)
+        if tune:
+            if switch:
+                self.fg_w, self.bg_w = self.bg_w, 0.0
+            self.n_adapt += 1
+        self.draw += 1
+        self.total_leapfrogs += n_leap.value
+        return n_leap.value
+
+    def stop_tuning(self):
+        check(self.L.bgh_nuts_stop_tuning(self.eng.ctx, ctypes.byref(self.buf), ctypes.byref(self.cfg), self._stream()),
+              self.eng.ctx)
+
+    # ------------------------------------------------------------------ pm.sample
+    def sample(self, draws, tune, trace_dtype=None, progress=None):
+        """Runs tune + draws transitions; returns a dict with
+        ``trace``  torch tensor [draws, D, C] on the device (positions in the unconstrained space),
+        ``stats``  numpy float64 [tune + draws, 8, C] (STAT_NAMES), ``leapfrogs`` int64 [tune + draws],
+        ``seconds_tune`` / ``seconds_draws`` wall-clock, ``tune``."""
+        t = self.t
+        eng = self.eng
+        C = eng.C
+        dt = trace_dtype or t.float64
+        trace = t.empty((draws, eng.D, C), dtype=dt, device=eng.device)
+        stats = t.empty((tune + draws, NUTS_N_STATS, C), dtype=t.float64, device=eng.device)
+        leap = np.zeros(tune + draws, dtype=np.int64)
+        t.cuda.synchronize(eng.device)
+        t0 = time.perf_counter()
+        t_tune = 0.0
+        for i in range(tune + draws):
+            tuning = i < tune
+            if i == tune:
+                self.stop_tuning()
+                t.cuda.synchronize(eng.device)
+                t_tune = time.perf_counter() - t0
+            depth = EARLY_MAX_TREEDEPTH if (tuning and i < EARLY_DRAWS) else MAX_TREEDEPTH
+            leap[i] = self.transition(tuning, depth)
+            stats[i].copy_(self.stats[:, :C])
+            if not tuning:
+                trace[i - tune].copy_(self.q[:, :C])
+            if progress is not None and (i + 1) % progress == 0:
+                print("  draw %d/%d  leapfrogs/draw %.1f" % (i + 1, tune + draws, leap[max(0, i - progress + 1):i + 1].mean()),
+                      flush=True)
+        t.cuda.synchronize(eng.device)
+        total = time.perf_counter() - t0
+        if tune >= tune + draws:
+            t_tune = total
+        st = stats.cpu().numpy()
+        if np.any(st[:, 3] > 0):
+            pass   # divergences are reported by the caller (PyMC3 prints a warning)
+        return dict(trace=trace, stats=st, leapfrogs=leap, seconds_tune=t_tune, seconds_draws=total - t_tune, tune=tune)
+
+
+def smoke(engine, data):
+    """A few tuned transitions on a tiny problem (called by __graft_entry__.smoke)."""
+    from . import synth
+    s = NutsSampler(engine, seed=1)
+    s.init(synth.jittered_start(engine.D, engine.C, seed=2))
+    for i in range(6):
+        s.transition(True, 6)
+    engine.torch.cuda.synchronize()
+    lp = s.logp.cpu().numpy()
+    assert np.all(np.isfinite(lp)), lp
+    return lp

@@ -139,13 +139,99 @@ int bgh_set_profiling(bgh_ctx* ctx, int32_t enable);
 int bgh_kernel_time_ms(bgh_ctx* ctx, double* lik_ms, double* finalize_ms, int64_t* n, int32_t reset);
 
 /* Host-only planning (no device needed; used by the CPU tests): gid_sorted[M] ascending compact
- * gene ids -> offsets[n_groups+1], flags[n_groups] (bit0 head-partial, bit1 tail-partial) and the
- * CSR of genes whose sum is assembled from slot partials (slot s < n_groups: head slot of group
- * s; s >= n_groups: tail slot of group s - n_groups).  cap = capacity of the split_* buffers. */
-int bgh_debug_plan(int64_t M, const int32_t* gid_sorted, int32_t G, int32_t n_groups,
-                   int32_t first_partial, int32_t last_partial, int32_t* offsets, int32_t* flags,
+ * gene ids -> offsets[n_groups+1], flags[n_groups] (bit0 head-partial, bit1 tail-partial, bit2
+ * exclusive CTA, bit3 prior owner) with n_groups = n_cta * groups_per_cta, and the CSR of genes
+ * whose sum is assembled from slot partials (slot s < n_groups: head slot of group s; s < 2
+ * n_groups: tail slot of group s - n_groups; else CTA slot s - 2 n_groups).  cap = capacity of
+ * the split_* buffers. */
+int bgh_debug_plan(int64_t M, const int32_t* gid_sorted, int32_t G, int32_t n_cta,
+                   int32_t groups_per_cta, int32_t first_partial, int32_t last_partial, int32_t* offsets, int32_t* flags,
                    int32_t* n_split, int32_t* split_gene, int32_t* split_ptr, int32_t* split_slots,
                    int32_t cap);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched-chain NUTS (replaces pm.sample(..., nuts_kwargs=dict(target_accept=0.90)),
+ * gene_regression.py:100-106 / heritability.py:56-62; PyMC3 3.6 semantics).
+ * The caller (the PyTorch host driver) owns all sampler memory and passes it as plain pointers:
+ *   state    double[BGH_NUTS_N_SLOTS][D][Cp]   vector slots; the caller reads/writes slots
+ *                                              Q (current position), GRAD, VAR (mass-matrix diagonal)
+ *                                              and the four adaptation slots, the rest is scratch
+ *   ckpt     double[2][BGH_NUTS_MAX_DEPTH][D][Cp]
+ *   sc       double[BGH_NUTS_N_SC][Cp]         per-chain scalars (EPS = step size, LOGP = logp(Q))
+ *   fl       int32 [BGH_NUTS_N_FL][Cp]
+ *   partials double[bgh_nuts_vec_blocks()][BGH_NUTS_MAX_PARTIALS][Cp]
+ *   sums     double[BGH_NUTS_MAX_PARTIALS][Cp]
+ *   logp_w   double[Cp]
+ *   stats    double[BGH_NUTS_N_STATS][Cp]      {depth, mean_tree_accept, tree_size, diverging, energy,
+ *                                               step_size, model_logp, max_energy_error} of the last transition
+ *   n_active_dev / n_active_host: one int32 on the device / in pinned host memory
+ * ------------------------------------------------------------------------------------------ */
+#define BGH_NUTS_MAX_DEPTH 10
+#define BGH_NUTS_MAX_PARTIALS (1 + 2 * BGH_NUTS_MAX_DEPTH)
+#define BGH_NUTS_N_SLOTS 20
+#define BGH_NUTS_SLOT_Q 0
+#define BGH_NUTS_SLOT_GRAD 1
+#define BGH_NUTS_SLOT_VAR 2
+#define BGH_NUTS_SLOT_FG_MEAN 16
+#define BGH_NUTS_SLOT_FG_RAW 17
+#define BGH_NUTS_SLOT_BG_MEAN 18
+#define BGH_NUTS_SLOT_BG_RAW 19
+#define BGH_NUTS_N_SC 16
+#define BGH_NUTS_SC_EPS 0
+#define BGH_NUTS_SC_LOGP 1
+#define BGH_NUTS_N_FL 11
+#define BGH_NUTS_N_STATS 8
+
+typedef struct bgh_nuts_buffers {
+    double* state;
+    double* ckpt;
+    double* sc;
+    int32_t* fl;
+    double* partials;
+    double* sums;
+    double* logp_w;
+    double* stats;
+    int32_t* n_active_dev;
+    int32_t* n_active_host;
+} bgh_nuts_buffers;
+
+typedef struct bgh_nuts_cfg {
+    uint64_t seed;          /* Philox key; chains and draws select the counter */
+    double target_accept;   /* 0.90 in the reference (gene_regression.py:105) */
+    double step_scale;      /* 0.25: initial step = step_scale / D^(1/4) [PyMC3 BaseHMC] */
+    double emax;            /* 1000: divergence threshold */
+    double da_gamma, da_kappa, da_t0;   /* 0.05, 0.75, 10 */
+    int32_t n_dim_total;    /* D over all ranks (step-size rule); 0 => bgh_dim(ctx) */
+    int32_t coord_offset;   /* global index of this rank's first coordinate */
+    int32_t reserved[4];
+} bgh_nuts_cfg;
+
+void bgh_nuts_cfg_default(bgh_nuts_cfg* cfg);
+int32_t bgh_nuts_vec_blocks(const bgh_ctx* ctx);
+
+/* Evaluates logp/grad at state[Q] into state[GRAD] / sc[LOGP] and initialises the step-size
+ * adaptation.  The caller has filled Q, VAR (ones), FG_MEAN (mean of the chains' starts), FG_RAW
+ * (10 * ones), BG_* (zeros) — PyMC3's init='jitter+adapt_diag'. */
+int bgh_nuts_init(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nuts_cfg* cfg, void* stream);
+
+/* One NUTS transition of every chain.  tune != 0: step-size and mass-matrix adaptation run after
+ * the transition; fg_weight / bg_weight are the estimator weights after adding this draw and
+ * switch_window != 0 swaps the estimators (quadpotential.QuadPotentialDiagAdapt.update, driven by
+ * the host because the schedule is identical for all chains).  Synchronises the stream once per
+ * tree doubling (to learn whether any chain is still growing its tree).  *n_leapfrogs receives the
+ * number of batched logp+grad evaluations. */
+int bgh_nuts_transition(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nuts_cfg* cfg, int64_t draw,
+                        int32_t tune, int32_t max_treedepth, double fg_weight, double bg_weight,
+                        int32_t switch_window, void* stream, int32_t* n_leapfrogs);
+
+/* End of tuning: step size <- exp(log_step_bar) (DualAverageAdaptation.current(tune=False)). */
+int bgh_nuts_stop_tuning(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nuts_cfg* cfg, void* stream);
+
+/* Tools only: per-warp phase timestamps (globaltimer ns) of the likelihood kernel.  enable != 0
+ * allocates the trace buffer; out (optional) receives the last launch's
+ * [chain_blocks * n_cta * 16][8] u64 words {t_enter, t_setup_done, t_stream_done, t_barrier,
+ * t_exit, -, -, smid}. */
+int bgh_debug_trace(bgh_ctx* ctx, int32_t enable, uint64_t* out, int64_t n_words);
 
 /* FP64 pipe microbenchmark (dependent-free DFMA streams on every SM): returns achieved
  * G DFMA-lane-instructions / s, the compute roof of the likelihood kernel at large C. */

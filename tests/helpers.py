@@ -13,22 +13,35 @@ def grad_rel_err(g, g_ref):
 
 def emulate_plan_gene_sums(plan, gid_sorted, values, G):
     """Per-gene sums of `values` computed the way lik_kernel + finalize_kernel assemble them:
-    sequential accumulation per group, interior genes stored directly, partial genes through
-    head/tail slots that are summed in split-list order."""
+    sequential accumulation per group; interior genes stored directly; partial genes through
+    head/tail slots; groups of exclusive CTAs (one huge gene) reduced into one CTA slot; the split
+    lists then sum the slots in order."""
     off, flags = plan["off"], plan["flags"]
-    NG = len(flags)
-    slots = np.full(2 * NG, np.nan)
+    NG, gpc = len(flags), plan["groups_per_cta"]
+    n_cta = NG // gpc
+    slots = np.full(2 * NG + n_cta, np.nan)
     direct = np.full(G, np.nan)
     owners = np.zeros(G, dtype=np.int64)
     for v in range(NG):
         a, b = int(off[v]), int(off[v + 1])
+        excl = bool(flags[v] & 4)
+        cta = v // gpc
+        if excl and np.isnan(slots[2 * NG + cta]):
+            slots[2 * NG + cta] = 0.0
         if a >= b:
+            continue
+        if excl:
+            assert gid_sorted[a] == gid_sorted[b - 1], "exclusive group spans genes"
+            assert all(flags[cta * gpc:(cta + 1) * gpc] & 4), "exclusive flag must be CTA-uniform"
+            slots[2 * NG + cta] += float(np.sum(values[a:b]))
+            if flags[v] & 8:
+                owners[gid_sorted[a]] += 1
             continue
         head, tail = bool(flags[v] & 1), bool(flags[v] & 2)
         g_first = gid_sorted[a]
         cur, acc = g_first, 0.0
 
-        def flush(final, cur=None, acc=None):
+        def flush(final, cur, acc):
             to_head = (cur == g_first) and head
             to_tail = (not to_head) and final and tail
             if to_head:
@@ -48,9 +61,13 @@ def emulate_plan_gene_sums(plan, gid_sorted, values, G):
             acc += values[j]
         flush(True, cur, acc)
     out = direct.copy()
+    used = np.zeros(len(slots), dtype=bool)
     for k, g in enumerate(plan["split_gene"]):
         s = plan["split_slots"][plan["split_ptr"][k]:plan["split_ptr"][k + 1]]
         assert np.isnan(direct[g]), "split gene also written directly"
         assert not np.any(np.isnan(slots[s])), "split list reads an unwritten slot"
+        assert not np.any(used[s]), "slot listed twice"
+        used[s] = True
         out[g] = float(np.sum(slots[s]))
+    assert np.array_equal(used, ~np.isnan(slots)), "a written slot is not read by any split list"
     return out, owners
