@@ -1,0 +1,140 @@
+"""``analyse_normal`` — drop-in for ref: baghera_tool/gene_regression.py:30-180 on the B200 path.
+
+Same positional signature, same side effects (summary CSV, results-log lines) and the same returned
+DataFrame columns; the ``with pm.Model()`` block and ``pm.sample`` are replaced by the CUDA engine
+(engine.Engine) and the batched NUTS driver (sampler.NutsSampler).  The posterior tables are
+computed on the device from the stored trace (K6), not from an in-RAM PyMC3 trace.
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import pandas as pd
+
+from . import stats as st
+
+# run-time options that have no slot in the reference signature (set by command / cli)
+OPTIONS = dict(device=0, seed=20211, trace_dtype="float64", progress=None)
+
+
+def build_gene_index(snp_dataset):
+    """ref: gene_regression.py:56-71 — cat[j] = rank of SNP j's gene label in sorted label order,
+    Mg = SNPs per gene, genes = labels (groupby iterates in sorted label order, Q6)."""
+    codes, genes = pd.factorize(snp_dataset["gene"], sort=True)
+    cat = codes.astype(np.int64)
+    Mg = np.bincount(cat, minlength=len(genes)).astype(np.int64)
+    return cat, Mg, [str(g) for g in genes]
+
+
+def device_quantiles(x, qs):
+    """numpy.percentile(..., interpolation='linear') along dim 0 of a device tensor x[N, K]."""
+    import torch
+    xs, _ = torch.sort(x, dim=0)
+    n = xs.shape[0]
+    out = []
+    for q in qs:
+        pos = (n - 1) * (q / 100.0)
+        lo = int(np.floor(pos))
+        hi = min(lo + 1, n - 1)
+        w = pos - lo
+        out.append(xs[lo] * (1.0 - w) + xs[hi] * w)
+    return out
+
+
+def gene_posterior_table(trace, genes, chunk=512):
+    """Per-gene posterior statistics (ref: gene_regression.py:165-177) from the device trace
+    [draws, D, C]: P = mean(beta - mi > 0), bg_mean/median/var/5perc/95perc over all draws and chains."""
+    import torch
+    draws, D, C = trace.shape
+    G = D - 3
+    mi = torch.sigmoid(trace[:, 2, :].double())                     # [draws, C]
+    cols = {k: np.empty(G) for k in ("P", "bg_mean", "bg_median", "bg_var", "bg_5perc", "bg_95perc")}
+    for g0 in range(0, G, chunk):
+        g1 = min(G, g0 + chunk)
+        b = trace[:, 3 + g0:3 + g1, :].double()                     # [draws, g, C]
+        P = ((b - mi[:, None, :]) > 0).double().mean(dim=(0, 2))
+        flat = b.permute(0, 2, 1).reshape(draws * C, g1 - g0)
+        q5, q50, q95 = device_quantiles(flat, (5.0, 50.0, 95.0))
+        cols["P"][g0:g1] = P.cpu().numpy()
+        cols["bg_mean"][g0:g1] = flat.mean(dim=0).cpu().numpy()
+        cols["bg_var"][g0:g1] = flat.var(dim=0, unbiased=False).cpu().numpy()
+        cols["bg_median"][g0:g1] = q50.cpu().numpy()
+        cols["bg_5perc"][g0:g1] = q5.cpu().numpy()
+        cols["bg_95perc"][g0:g1] = q95.cpu().numpy()
+    df = pd.DataFrame({"name": genes})
+    for k in ("P", "bg_mean", "bg_median", "bg_var", "bg_5perc", "bg_95perc"):
+        df[k] = cols[k]
+    return df
+
+
+def analyse_normal(snps_object, output_summary_filename, output_logger, SWEEPS, TUNE, CHAINS, CORES, N_1kG,
+                   fix_intercept=False):
+    """Bayesian hierarchical regression with the normal model (ref: gene_regression.py:30-180).
+
+    CORES is accepted for signature compatibility; chains run as one batch on the GPU."""
+    import torch
+
+    from . import synth
+    from .engine import Engine
+    from .sampler import NutsSampler
+
+    snp_dataset = snps_object.table.copy().reset_index(drop=True)
+    n_patients = snps_object.n_patients
+    cat, Mg, genes = build_gene_index(snp_dataset)
+    G = len(genes)
+
+    logging.info("Model Evaluation Started")
+    logging.info("Average stats: %f" % np.mean(snps_object.table["stats"].values))
+
+    c = float(n_patients) / float(N_1kG)
+    eng = Engine(snp_dataset["stats"].values.astype(np.float32), snp_dataset["l"].values.astype(np.float32),
+                 cat.astype(np.int32), G, c, int(CHAINS), model="gene", fix_intercept=bool(fix_intercept),
+                 device=OPTIONS["device"])
+    sampler = NutsSampler(eng, seed=OPTIONS["seed"], target_accept=0.90)      # nuts_kwargs=dict(target_accept=0.90)
+    sampler.init(synth.jittered_start(eng.D, int(CHAINS), seed=OPTIONS["seed"] + 1, model="gene"))
+    dt = torch.float32 if OPTIONS["trace_dtype"] == "float32" else torch.float64
+    out = sampler.sample(int(SWEEPS), int(TUNE), trace_dtype=dt, progress=OPTIONS["progress"])
+    trace = out["trace"]                                           # [draws, D, C], unconstrained space
+    n_div = int(out["stats"][int(TUNE):, 3].sum())
+    if n_div:
+        logging.warning("There were %d divergences after tuning. Increase `target_accept` or reparameterize." % n_div)
+
+    tW = torch.exp(trace[:, 0, :].double()).cpu().numpy()           # W  = exp(W_log__)
+    te = trace[:, 1, :].double().cpu().numpy()
+    tmi = torch.sigmoid(trace[:, 2, :].double()).cpu().numpy()      # mi = sigmoid(mi_logodds__)
+    w = torch.as_tensor(Mg / float(N_1kG), dtype=torch.float64, device=trace.device)
+    therTOT = torch.einsum("dgc,g->dc", trace[:, 3:, :].double(), w).cpu().numpy()   # (:83)
+
+    if CHAINS > 1:
+        logging.info("evaluating Gelman-Rubin")
+        GR = {"mi": st.gelman_rubin(tmi)}
+        output_logger.info("DIAGNOSTIC (gelman-rubin) " + str(GR) + "\n\t"
+                           + "(If this number is >> 1 the method has some convergence problem, \n\t try increasing the number of s and b)")
+
+    logging.info("Writing output")
+    su = st.summary({"mi": tmi, "herTOT": therTOT, "e": te, "W": tW})         # (:120-125)
+    su.to_csv(output_summary_filename, sep=",", mode="w")
+
+    output_logger.info(" Intercept: " + str(np.mean(te)) + " (sd= " + str(np.std(te)) + ")\n")
+    output_logger.info(" W: " + str(np.mean(tW)) + " (sd= " + str(np.std(tW)) + ")\n")
+    output_logger.info(" heritability from genes: " + str(np.median(therTOT)) + " (sd= " + str(np.std(therTOT)) + ")\n")
+    mi_mean, mi_median, mi_std = np.mean(tmi), np.median(tmi), np.std(tmi)
+    mi_5perc, mi_95perc = np.percentile(tmi, 5), np.percentile(tmi, 95)
+    output_logger.info(" Heritability: " + str(mi_mean) + " (std= " + str(mi_std) + ")\n" + "[ 5th perc= "
+                       + str(mi_5perc) + "," + " 95 perc= " + str(mi_95perc) + "]\n")
+
+    df = gene_posterior_table(trace, genes)
+    df["mi_mean"] = mi_mean
+    df["mi_median"] = mi_median
+    analyse_normal.last_run = dict(seconds_tune=out["seconds_tune"], seconds_draws=out["seconds_draws"],
+                                   leapfrogs=out["leapfrogs"], stats=out["stats"], kernel_launches=eng.launch_count)
+    eng.close()
+    logging.info("analysis done")
+    return df
+
+
+def analyse_gamma(*args, **kwargs):
+    raise NotImplementedError(
+        "-m gamma (ref: gene_regression.py:183-325) is not on the B200 path yet: it shares the likelihood kernel "
+        "but needs the Gamma-prior closing kernel (SURVEY §8f rank 3). Use -m normal.")

@@ -124,7 +124,7 @@ def make_snp_table(M: int, G: int, seed: int = SEED, neg_ld_frac: float = 0.002,
     """Annotated SNP table as a pandas DataFrame (schema of ref: docs/createdata.rst:45-47).
 
     ``l`` is the *raw* LD score (the filter adds 1 and clamps negatives, Q7); ``z`` is signed
-    with ``z**2`` following the model; NonCoding SNPs carry ``gene = NaN``
+    with ``E[z**2]`` following the model's mean; NonCoding SNPs carry ``gene = NaN``
     (ref: baghera_tool/snps.py:98-102).
     """
     import pandas as pd
@@ -144,9 +144,9 @@ def make_snp_table(M: int, G: int, seed: int = SEED, neg_ld_frac: float = 0.002,
     hot[-1] = False
     beta[hot] = mi0 + 1.0
     c = N_PATIENTS / N_1KG
-    stats = e0 + c * l_eff * beta[gidx] + np.sqrt(l_eff) * rng.standard_normal(M)
-    stats = np.maximum(stats, 1e-6)
-    z = np.sqrt(stats) * rng.choice([-1.0, 1.0], size=M)
+    # z ~ N(0, sd^2) with sd^2 = e0 + c*l*beta, so that E[z^2] follows the model's mean structure
+    # (chi2 statistics cannot be negative, unlike draws from the Normal likelihood itself)
+    z = rng.standard_normal(M) * np.sqrt(np.maximum(e0 + c * l_eff * beta[gidx], 0.05))
     maf = rng.uniform(0.011, 0.5, size=M)
     low = rng.random(M) < low_maf_frac
     maf[low] = rng.uniform(0.001, 0.0099, size=int(low.sum()))
