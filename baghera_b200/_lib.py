@@ -89,6 +89,7 @@ SIGNATURES = {
     "bgh_payload_rows": (_i32, [_vp]),
     "bgh_upload": (_i32, [_vp, _vp, _vp, _vp]),
     "bgh_lik_const": (_dbl, [_vp]),
+    "bgh_set_lik_const": (_i32, [_vp, _dbl]),
     "bgh_logp_grad": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "bgh_logp_grad_local": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "bgh_logp_grad_finish": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),

@@ -434,6 +434,13 @@ int32_t bgh_dim(const bgh_ctx* ctx) { return ctx ? ctx->D : 0; }
 int32_t bgh_chain_stride(const bgh_ctx* ctx) { return ctx ? ctx->Cp : 0; }
 int32_t bgh_payload_rows(const bgh_ctx* ctx) { return ctx ? 4 + ctx->cfg.n_shared_rows : 0; }
 double bgh_lik_const(const bgh_ctx* ctx) { return ctx ? ctx->lik_const : 0.0; }
+int bgh_set_lik_const(bgh_ctx* ctx, double total)
+{
+    if (!ctx || !isfinite(total)) return fail(ctx, BGH_EINVAL, "bgh_set_lik_const: bad argument");
+    if (!ctx->uploaded) return fail(ctx, BGH_ESTATE, "bgh_set_lik_const: call bgh_upload first");
+    ctx->lik_const = total;
+    return BGH_OK;
+}
 int32_t bgh_n_groups(const bgh_ctx* ctx) { return ctx ? ctx->n_groups : 0; }
 int32_t bgh_n_split_genes(const bgh_ctx* ctx) { return ctx ? (int32_t)ctx->plan.split_gene.size() : 0; }
 int64_t bgh_launch_count(const bgh_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -135,6 +135,11 @@ class Engine:
         check(self.L.bgh_logp_grad_host_stream(self.ctx, int(n), ctypes.c_void_p(q_ptr), ctypes.c_void_p(logp_ptr),
                                                ctypes.c_void_p(grad_ptr)), self.ctx)
 
+    def set_lik_const(self, total):
+        """Sharded runs: install the all-reduced normalising constant (sum over ranks of lik_const)."""
+        check(self.L.bgh_set_lik_const(self.ctx, float(total)), self.ctx)
+        self.lik_const = float(total)
+
     # ------------------------------------------------------------------ introspection
     def partition(self):
         n = int(self.L.bgh_n_groups(self.ctx)) + 1

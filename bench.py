@@ -93,35 +93,6 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
-def shard_dataset(d, rank, world):
-    """Gene-block sharding of the gene-sorted SNP array: contiguous, balanced by SNP count.
-
-    Returns (chi2, ld, local_gene_id, n_local_genes, shard_cfg, gene_lo).  A gene cut by a rank
-    boundary is replicated on the ranks it touches; its residual sum travels in the all-reduce payload.
-    """
-    order = np.argsort(d.gene_id, kind="stable")
-    gid = d.gene_id[order]
-    M = gid.shape[0]
-    cuts = [int(round(k * M / world)) for k in range(world + 1)]
-    shared = []                                   # genes cut by a rank boundary, in order
-    for k in range(1, world):
-        x = cuts[k]
-        if 0 < x < M and gid[x - 1] == gid[x]:
-            g = int(gid[x])
-            if not shared or shared[-1] != g:
-                shared.append(g)
-    a, b = cuts[rank], cuts[rank + 1]
-    g_lo, g_hi = int(gid[a]), int(gid[b - 1])
-    first_partial = a > 0 and gid[a - 1] == gid[a]
-    last_partial = b < M and gid[b] == gid[b - 1]
-    cfg = dict(n_genes_total=d.G, n_shared_rows=len(shared),
-               first_gene_partial=int(first_partial), last_gene_partial=int(last_partial),
-               first_gene_row=shared.index(g_lo) if (first_partial or (g_lo in shared)) and g_lo in shared else -1,
-               last_gene_row=shared.index(g_hi) if g_hi in shared else -1)
-    sel = order[a:b]
-    return d.chi2[sel], d.ld[sel], (gid[a:b] - g_lo).astype(np.int32), g_hi - g_lo + 1, cfg, g_lo
-
-
 def run_cpu_baseline(d, C, target_seconds=10.0, n_threads=0):
     """Times the C restatement of the reference CPU path (oracle/oracle_c.c) on the host cores."""
     from oracle.c_oracle import COracle, num_threads
@@ -132,7 +103,7 @@ def run_cpu_baseline(d, C, target_seconds=10.0, n_threads=0):
     t0 = time.perf_counter()
     co.logp_grad_batch(Q, n_threads=T)
     t1 = time.perf_counter() - t0
-    reps = int(max(1, min(200, target_seconds / max(t1, 1e-4))))
+    reps = int(max(1, min(5000, target_seconds / max(t1, 1e-4))))
     Qb = np.tile(Q, (reps, 1))
     t0 = time.perf_counter()
     co.logp_grad_batch(Qb, n_threads=T)
@@ -142,6 +113,42 @@ def run_cpu_baseline(d, C, target_seconds=10.0, n_threads=0):
             "sample": "%d chain-evals of the full %dx%d dataset (one chain per thread, %d threads, %.1f s); "
                       "C restatement of the Theano op sequence, not PyMC3 itself" % (n, d.M, d.G, T, dt),
             "ms_per_chain_eval_per_core": dt / n * T * 1e3}
+
+
+def run_sampler_section(eng, args, C):
+    """ESS/s of the batched NUTS driver on the same dataset (secondary metric of BASELINE.json)."""
+    import torch
+    from baghera_b200 import stats as st
+    from baghera_b200 import synth
+    from baghera_b200.sampler import NutsSampler
+    smp = NutsSampler(eng, seed=1)
+    smp.init(synth.jittered_start(eng.D, C, seed=2))
+    l0 = eng.launch_count
+    out = smp.sample(args.sampler_draws, args.sampler_tune, trace_dtype=torch.float32)
+    tr = out["trace"]
+    tune = args.sampler_tune
+    secs = out["seconds_draws"]
+    scal = {"W": torch.exp(tr[:, 0, :].double()).cpu().numpy(), "e": tr[:, 1, :].double().cpu().numpy(),
+            "mi": torch.sigmoid(tr[:, 2, :].double()).cpu().numpy()}
+    ess = {k: st.effective_n(v) for k, v in scal.items()}
+    rhat = {k: st.gelman_rubin(v) for k, v in scal.items()}
+    rng = np.random.default_rng(0)
+    genes = rng.choice(eng.D - 3, size=min(64, eng.D - 3), replace=False) + 3
+    beta_ess = [st.effective_n(tr[:, int(g), :].double().cpu().numpy()) for g in genes]
+    post = out["stats"][tune:]
+    leap = out["leapfrogs"]
+    return {
+        "chains": C, "tune": tune, "draws": args.sampler_draws,
+        "seconds_tune": out["seconds_tune"], "seconds_draws": secs,
+        "ess_min_scalar": min(ess.values()), "ess_per_sec": min(ess.values()) / secs, "ess": ess, "rhat": rhat,
+        "ess_median_beta": float(np.median(beta_ess)), "ess_median_beta_per_sec": float(np.median(beta_ess)) / secs,
+        "leapfrogs_per_draw_post_tune": float(leap[tune:].mean()), "leapfrogs_total": int(leap.sum()),
+        "chain_leapfrogs_per_sec_post_tune": float(leap[tune:].sum()) * C / secs,
+        "mean_tree_accept": float(post[:, 1].mean()), "divergences": int(post[:, 3].sum()),
+        "mean_depth": float(post[:, 0].mean()), "gpu_launches": eng.launch_count - l0,
+        "estimator": "pymc3 3.6 effective_n (Geyer initial sequences), post-tune draws only",
+        "note": "short run: %d tuning draws do not fully converge the 15k-dim mass matrix; ESS/s is indicative" % tune,
+    }
 
 
 def bench_reference(args, wl):
@@ -204,10 +211,13 @@ def bench_gpu(args, wl):
         q_dev = eng.to_device_layout(Q)
         g_lo = 0
     else:
-        chi2, ld, gid, G_loc, scfg, g_lo = shard_dataset(d, rank, world)
-        eng = Engine(chi2, ld, gid, G_loc, d.c, C, device=local_rank, shard=scfg)
-        Qloc = np.concatenate([Q[:, :3], Q[:, 3 + g_lo: 3 + g_lo + G_loc]], axis=1)
-        q_dev = eng.to_device_layout(Qloc)
+        from baghera_b200.sharding import shard_dataset
+        sh = shard_dataset(d.chi2, d.ld, d.gene_id, G, rank, world)
+        eng = Engine(sh.chi2, sh.ld, sh.gene_id, sh.n_genes, d.c, C, device=local_rank, shard=sh.cfg)
+        q_dev = eng.to_device_layout(sh.local_q(Q))
+        lc = torch.tensor([eng.lik_const], dtype=torch.float64, device=dev)
+        dist.all_reduce(lc)
+        eng.set_lik_const(float(lc.item()))
     Cp = eng.Cp
     logp = torch.empty(Cp, dtype=torch.float64, device=dev)
     grad = torch.zeros_like(q_dev)
@@ -331,6 +341,8 @@ def bench_gpu(args, wl):
         assert np.allclose(lh[-1].numpy(), lp_dev, rtol=1e-12), "e2e result differs from device path"
     elif rank == 0:
         line["e2e"] = None
+    if rank == 0 and world == 1 and not args.no_sampler:
+        line["sampler"] = run_sampler_section(eng, args, C)
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = run_cpu_baseline(d, C, target_seconds=args.cpu_seconds)
     if rank == 0:
@@ -350,6 +362,9 @@ def main():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-sampler", action="store_true", help="skip the ESS/s section")
+    ap.add_argument("--sampler-tune", type=int, default=300)
+    ap.add_argument("--sampler-draws", type=int, default=200)
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -100,6 +100,9 @@ int bgh_upload(bgh_ctx* ctx, const float* chi2, const float* ld, const int32_t* 
 
 /* sum_j -1/2 log(2 pi l_j), the chain-independent constant of the likelihood (after upload). */
 double bgh_lik_const(const bgh_ctx* ctx);
+/* Sharded runs: every rank uploads its shard, the ranks all-reduce (sum) bgh_lik_const once and
+ * install the total here so that each rank's logp carries the full constant. */
+int bgh_set_lik_const(bgh_ctx* ctx, double total);
 
 /* B1' on the device: q, grad are [D][Cp], logp is [Cp]; async on `stream`.
  * Single-rank contexts only (n_shared_rows == 0). */

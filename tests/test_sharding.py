@@ -1,0 +1,175 @@
+"""Multi-rank path.
+
+* CPU, world_size 2 over gloo: shard planning, payload layout and the all-reduce plumbing, with the
+  local pass emulated from the oracle (kernels cannot run without a GPU).
+* GPU (-m gpu): the real kernels with R ranks emulated one after the other on ONE device — the ranks'
+  payloads are summed on the device exactly as the NCCL all-reduce would (B200_PROFILING.md: "emulate
+  the ranks ... or test the multi-rank path on the CPU"; never wait across launches on one GPU).
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from baghera_b200 import synth
+from baghera_b200.sharding import assemble_global_grad, shard_dataset
+from oracle import model_oracle as mo
+from helpers import REL_TOL, grad_rel_err
+
+
+def _payload_and_grad_from_oracle(sh, Qloc, c, fix=False):
+    """What bgh_logp_grad_local produces for one rank, restated with numpy: payload rows
+    {sum r^2/l, sum r/l, sum(beta-mi) [owned genes], sum(beta-mi)^2, shared-gene residual sums} and the
+    gradient rows of the non-shared local genes."""
+    C = Qloc.shape[0]
+    chi2, ld = sh.chi2.astype(np.float64), sh.ld.astype(np.float64)
+    payload = np.zeros((4 + sh.cfg["n_shared_rows"], C))
+    grad = np.full((C, 3 + sh.n_genes), np.nan)
+    for i in range(C):
+        q = Qloc[i]
+        W, e, mi = np.exp(q[0]), (1.0 if fix else q[1]), 1 / (1 + np.exp(-q[2]))
+        beta = q[3:]
+        r = chi2 - e - c * ld * beta[sh.gene_id]
+        payload[0, i] = np.sum(r * r / ld)
+        payload[1, i] = np.sum(r / ld)
+        owned = np.ones(sh.n_genes, bool)
+        if sh.cfg["first_gene_partial"]:
+            owned[0] = False                      # the gene's first SNP lives on a previous rank
+        d = beta - mi
+        payload[2, i] = np.sum(d[owned])
+        payload[3, i] = np.sum(d[owned] ** 2)
+        sums = np.bincount(sh.gene_id, weights=r, minlength=sh.n_genes)
+        g = c * sums - d / W ** 2
+        if sh.cfg["first_gene_row"] >= 0:
+            payload[4 + sh.cfg["first_gene_row"], i] += sums[0]
+            g[0] = np.nan
+        if sh.cfg["last_gene_row"] >= 0 and not (sh.n_genes == 1 and sh.cfg["first_gene_row"] >= 0):
+            payload[4 + sh.cfg["last_gene_row"], i] += sums[-1]
+            g[-1] = np.nan
+        grad[i, 3:] = g
+    return payload, grad
+
+
+def _finish_from_payload(sh, Qloc, payload, grad, c, G_total, lik_const_total, fix=False):
+    C = Qloc.shape[0]
+    lp = np.empty(C)
+    for i in range(C):
+        q = Qloc[i]
+        W, e, mi = np.exp(q[0]), q[1], 1 / (1 + np.exp(-q[2]))
+        A_ll, A_e, S1, S2 = payload[0, i], payload[1, i], payload[2, i], payload[3, i]
+        lp[i] = ((-1 / W - 2 * np.log(W)) + q[0] - 0.5 * (e - 1) ** 2 - 0.5 * mo.LOG_2PI + np.log(mi) + np.log1p(-mi)
+                 - S2 / (2 * W * W) - G_total * np.log(W) - 0.5 * G_total * mo.LOG_2PI - 0.5 * A_ll + lik_const_total)
+        grad[i, 0] = 1 / W - 1 + S2 / W ** 2 - G_total
+        grad[i, 1] = -(e - 1) + (0.0 if fix else A_e)
+        grad[i, 2] = 1 - 2 * mi + mi * (1 - mi) * S1 / W ** 2
+        for row, gl in ((sh.cfg["first_gene_row"], 0), (sh.cfg["last_gene_row"], sh.n_genes - 1)):
+            if row >= 0:
+                grad[i, 3 + gl] = c * payload[4 + row, i] - (q[3 + gl] - mi) / W ** 2
+    return lp, grad
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_shard_plan(world):
+    d = synth.make_arrays(20_000, 200)
+    shards = [shard_dataset(d.chi2, d.ld, d.gene_id, d.G, r, world) for r in range(world)]
+    assert sum(len(s.chi2) for s in shards) == d.M
+    lens = [len(s.chi2) for s in shards]
+    assert max(lens) - min(lens) <= 1                                   # balanced by SNP count
+    for r, s in enumerate(shards):
+        assert s.gene_id.min() == 0 and s.gene_id.max() == s.n_genes - 1 and np.all(np.diff(s.gene_id) >= 0)
+        if r > 0:
+            prev = shards[r - 1]
+            assert bool(s.cfg["first_gene_partial"]) == (prev.gene_lo + prev.n_genes - 1 == s.gene_lo)
+            assert bool(prev.cfg["last_gene_partial"]) == bool(s.cfg["first_gene_partial"])
+        assert s.cfg["n_shared_rows"] == len(s.shared_genes)
+    # NonCoding (45% of SNPs, last label) must be shared once world >= 3
+    if world >= 3:
+        assert d.G - 1 in shards[-1].shared_genes
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        d = synth.make_arrays(20_000, 200)
+        C = 3
+        Q = synth.jittered_start(d.G + 3, C, seed=4)
+        sh = shard_dataset(d.chi2, d.ld, d.gene_id, d.G, rank, world)
+        Qloc = sh.local_q(Q)
+        payload, grad = _payload_and_grad_from_oracle(sh, Qloc, d.c)
+        t = torch.from_numpy(payload)
+        dist.all_reduce(t)                                            # the per-step exchange
+        const = torch.tensor([mo.lik_const(sh.ld.astype(np.float64))], dtype=torch.float64)
+        dist.all_reduce(const)                                        # one-off: total normalising constant
+        lp, grad = _finish_from_payload(sh, Qloc, t.numpy(), grad, d.c, d.G, float(const[0]))
+        q.put((rank, lp, grad, sh))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_matches_unsharded_oracle():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world = 2
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    d = synth.make_arrays(20_000, 200)
+    Q = synth.jittered_start(d.G + 3, 3, seed=4)
+    lp_ref, g_ref = mo.batch_closed(Q, d.chi2.astype(np.float64), d.ld.astype(np.float64), d.gene_id.astype(np.int64), d.c)
+    grads = assemble_global_grad([r[2] for r in res], [r[3] for r in res], d.G + 3)
+    for rank, lp, _, _ in res:
+        assert np.allclose(lp, lp_ref, rtol=1e-12)                     # every rank holds the same logp
+    for i in range(3):
+        assert grad_rel_err(grads[i], g_ref[i]) < 1e-10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,M,G", [(2, 20_000, 200), (4, 60_000, 300), (8, 1_100_000, 15_000)])
+def test_emulated_ranks_on_one_gpu(world, M, G):
+    import torch
+    from baghera_b200.engine import Engine
+    d = synth.make_arrays(M, G)
+    C = 64 if M > 100_000 else 8
+    Q = synth.jittered_start(d.G + 3, C, seed=6)
+    shards = [shard_dataset(d.chi2, d.ld, d.gene_id, d.G, r, world) for r in range(world)]
+    engines = [Engine(s.chi2, s.ld, s.gene_id, s.n_genes, d.c, C, shard=s.cfg) for s in shards]
+    Cp = engines[0].Cp
+    rows = engines[0].payload_rows
+    qs = [e.to_device_layout(s.local_q(Q)) for e, s in zip(engines, shards)]
+    grads = [torch.zeros_like(q) for q in qs]
+    payloads = [torch.zeros((rows, Cp), dtype=torch.float64, device="cuda") for _ in range(world)]
+    for e, q, g, p in zip(engines, qs, grads, payloads):
+        e.logp_grad_local(q, g, p)
+    total = torch.stack(payloads).sum(dim=0)                           # what ncclAllReduce(sum) delivers
+    const = sum(e.lik_const for e in engines)                          # one-off all-reduce at setup
+    lps = []
+    for e, q, g in zip(engines, qs, grads):
+        e.set_lik_const(const)
+        lp = torch.empty(Cp, dtype=torch.float64, device="cuda")
+        e.logp_grad_finish(q, total, lp, g)
+        lps.append(lp[:C].cpu().numpy())
+    torch.cuda.synchronize()
+    n_ref = C if M <= 100_000 else 2
+    lp_ref, g_ref = mo.batch_closed(Q[:n_ref], d.chi2.astype(np.float64), d.ld.astype(np.float64),
+                                    d.gene_id.astype(np.int64), d.c)
+    g_all = assemble_global_grad([e.from_device_layout(g).cpu().numpy() for e, g in zip(engines, grads)], shards, d.G + 3)
+    for lp in lps:
+        assert np.max(np.abs(lp[:n_ref] - lp_ref) / np.abs(lp_ref)) < REL_TOL
+    for i in range(n_ref):
+        assert grad_rel_err(g_all[i], g_ref[i]) < REL_TOL
+    for e in engines:
+        e.close()
