@@ -65,6 +65,12 @@ class bgh_nuts_cfg(ctypes.Structure):
     ]
 
 
+class bgh_nuts_async_buffers(ctypes.Structure):
+    _fields_ = [("base", bgh_nuts_buffers), ("afl", ctypes.c_void_p), ("trace", ctypes.c_void_p),
+                ("run_stats", ctypes.c_void_p), ("trace_f32", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+NUTS_ASYNC_N_FL, NUTS_ASYNC_N_SC, NUTS_ASYNC_PARTIALS = 24, 24, 24
 NUTS_MAX_DEPTH, NUTS_N_SLOTS, NUTS_N_SC, NUTS_N_FL, NUTS_N_STATS = 10, 20, 16, 11, 8
 NUTS_MAX_PARTIALS = 1 + 2 * NUTS_MAX_DEPTH
 NUTS_SLOT_Q, NUTS_SLOT_GRAD, NUTS_SLOT_VAR = 0, 1, 2
@@ -110,6 +116,8 @@ SIGNATURES = {
     "bgh_nuts_transition": (_i32, [_vp, ctypes.POINTER(bgh_nuts_buffers), ctypes.POINTER(bgh_nuts_cfg), _i64, _i32, _i32,
                                    _dbl, _dbl, _i32, _vp, _pi32]),
     "bgh_nuts_stop_tuning": (_i32, [_vp, ctypes.POINTER(bgh_nuts_buffers), ctypes.POINTER(bgh_nuts_cfg), _vp]),
+    "bgh_nuts_run": (_i32, [_vp, ctypes.POINTER(bgh_nuts_async_buffers), ctypes.POINTER(bgh_nuts_cfg), _i32, _i32, _i32,
+                            _vp, _pi64]),
     "bgh_debug_trace": (_i32, [_vp, _i32, _vp, _i64]),
     "bgh_debug_plan": (_i32, [_i64, _pi32, _i32, _i32, _i32, _i32, _i32, _pi32, _pi32, _pi32, _pi32, _pi32, _pi32, _i32]),
 }

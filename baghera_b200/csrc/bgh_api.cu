@@ -287,7 +287,7 @@ struct bgh_ctx {
     double* d_g_dc[kPipe] = {nullptr, nullptr};
     double* d_g_cd[kPipe] = {nullptr, nullptr};
     double* d_lp[kPipe] = {nullptr, nullptr};
-    cudaStream_t st_h2d = nullptr, st_cmp = nullptr, st_d2h = nullptr;
+    cudaStream_t st_h2d = nullptr, st_cmp = nullptr, st_d2h = nullptr, st_graph = nullptr;
     cudaEvent_t ev_up[kPipe] = {nullptr, nullptr}, ev_cmp[kPipe] = {nullptr, nullptr},
                 ev_dn[kPipe] = {nullptr, nullptr};
     // profiling
@@ -426,6 +426,7 @@ void bgh_destroy(bgh_ctx* ctx)
     if (ctx->st_h2d) cudaStreamDestroy(ctx->st_h2d);
     if (ctx->st_cmp) cudaStreamDestroy(ctx->st_cmp);
     if (ctx->st_d2h) cudaStreamDestroy(ctx->st_d2h);
+    if (ctx->st_graph) cudaStreamDestroy(ctx->st_graph);
     for (cudaEvent_t ev : ctx->prof_ev) cudaEventDestroy(ev);
     delete ctx;
 }
@@ -919,6 +920,78 @@ int bgh_nuts_transition(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nut
     ctx->launches += 1;
     if (n_leapfrogs) *n_leapfrogs = leapfrogs;
     return BGH_OK;
+}
+
+int bgh_nuts_run(bgh_ctx* ctx, const bgh_nuts_async_buffers* buf, const bgh_nuts_cfg* cfg, int32_t tune,
+                 int32_t draws, int32_t poll_ticks, void* stream, int64_t* n_ticks)
+{
+    if (!buf) return fail(ctx, BGH_EINVAL, "bgh_nuts_run: null argument");
+    AsyncParams a;
+    int rc = nuts_params(ctx, &buf->base, cfg, 0, &a.n);
+    if (rc != BGH_OK) return rc;
+    if (!buf->afl || (draws > 0 && !buf->trace) || tune < 0 || draws < 0 || tune + draws <= 0)
+        return fail(ctx, BGH_EINVAL, "bgh_nuts_run: bad argument");
+    if (ctx->Cp > 170) return fail(ctx, BGH_EINVAL, "bgh_nuts_run: at most 128 chains per context (use several contexts / GPUs)");
+    if (poll_ticks <= 0) poll_ticks = 64;
+    a.afl = buf->afl; a.trace = buf->trace; a.stats = buf->run_stats; a.n_finished = buf->base.n_active_dev;
+    a.trace_f32 = buf->trace_f32; a.tune = tune; a.draws = draws;
+    a.early_draws = 200; a.early_depth = 8; a.max_depth = kNutsMaxDepth; a.window = 101;
+    // stream capture is not allowed on the legacy default stream, which is what callers usually pass:
+    // run on the context's own stream, ordered after everything queued on the caller's stream
+    BGH_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    if (!ctx->st_graph) BGH_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->st_graph, cudaStreamNonBlocking));
+    BGH_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    cudaStream_t s = ctx->st_graph;
+    const size_t vec = (size_t)ctx->D * ctx->Cp;
+    double* const qw = buf->base.state + kSlotQW * vec;
+    double* const gw = buf->base.state + kSlotGW * vec;
+    const int Dtot = cfg->n_dim_total > 0 ? cfg->n_dim_total : ctx->D;
+    const double step0 = cfg->step_scale / pow((double)Dtot, 0.25);
+    BGH_CUDA(ctx, nuts_async_launch_init(a, step0, 10.0, s));
+    // working position must be finite for every (also padded / finished) chain: start it at the current point
+    BGH_CUDA(ctx, cudaMemcpyAsync(qw, buf->base.state + kSlotQP * vec, sizeof(double) * vec, cudaMemcpyDeviceToDevice, s));
+    ctx->launches += 1;
+
+    // one tick = pre, likelihood, finalize, post, scalar: captured once, replayed
+    const bool was_profiling = ctx->profiling;
+    ctx->profiling = false;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    BGH_CUDA(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+    cudaError_t e1 = nuts_async_launch_pre(a, s);
+    int rc2 = run_local(ctx, qw, buf->base.logp_w, gw, ctx->d_payload, true, s);
+    cudaError_t e2 = nuts_async_launch_post(a, s);
+    cudaError_t e3 = cudaStreamEndCapture(s, &graph);
+    ctx->launches -= 2;   // the capture itself launched nothing
+    ctx->profiling = was_profiling;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || rc2 != BGH_OK || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        return fail(ctx, BGH_ECUDA, std::string("bgh_nuts_run: graph capture failed: ") +
+                                        cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+    }
+    BGH_CUDA(ctx, cudaGraphInstantiate(&exec, graph, 0));
+    int64_t ticks = 0;
+    // a transition needs at most 2^10 - 1 leaves; bound the loop so that a logic error cannot hang the GPU
+    const int64_t max_ticks = (int64_t)(tune + draws) * 1024 + 1024;
+    int status = BGH_OK;
+    while (ticks < max_ticks) {
+        for (int i = 0; i < poll_ticks; ++i) {
+            cudaError_t e = cudaGraphLaunch(exec, s);
+            if (e != cudaSuccess) { status = fail(ctx, BGH_ECUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(e)); break; }
+        }
+        if (status != BGH_OK) break;
+        ticks += poll_ticks;
+        ctx->launches += 5 * (int64_t)poll_ticks;
+        cudaError_t e = cudaMemcpyAsync(buf->base.n_active_host, buf->base.n_active_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { status = fail(ctx, BGH_ECUDA, std::string("bgh_nuts_run: ") + cudaGetErrorString(e)); break; }
+        if (*buf->base.n_active_host >= ctx->cfg.n_chains) break;
+    }
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+    if (status == BGH_OK && ticks >= max_ticks) status = fail(ctx, BGH_ESTATE, "bgh_nuts_run: tick budget exhausted");
+    if (n_ticks) *n_ticks = ticks;
+    return status;
 }
 
 }  // extern "C"

@@ -66,6 +66,38 @@ cudaError_t nuts_launch_adapt_mass(const NutsParams& p, double fg_w, double bg_w
 cudaError_t nuts_launch_finish(const NutsParams& p, int tune, double* stats, cudaStream_t s);
 cudaError_t nuts_launch_stop_tuning(const NutsParams& p, cudaStream_t s);
 cudaError_t nuts_launch_init(const NutsParams& p, double step0, cudaStream_t s);
-constexpr int kNutsLaunchesPerLeaf = 3;   // leap1, leap2, leaf scalar (plus the likelihood + finalize)
+constexpr int kNutsLaunchesPerLeaf = 3;
+
+// ---- asynchronous per-chain state machine (bgh_nuts_run): control flags afl[k][Cp], scalars asc[k][Cp]
+constexpr int kAsyncPartials = 2 * kNutsMaxDepth + 4;   // kinetic, 2*depth sub-block dots, 2 whole-tree dots, kinetic0
+constexpr int kAqTree0 = 1 + 2 * kNutsMaxDepth;          // whole-tree dots live at [kAqTree0], [kAqTree0+1]
+constexpr int kAqKin0 = kAqTree0 + 2;
+enum : int {
+    kAfPhase = 0, kAfDepth, kAfLeaf, kAfDir, kAfDirPrev, kAfTake, kAfTakeTop, kAfMerge, kAfNew, kAfFirst, kAfRecSlot,
+    kAfAdapt, kAfSwitch, kAfStoreLevel, kAfLvlMin, kAfNLvl, kAfLastLeaf, kAfDraw, kAfDiverging, kAfTurning, kAfNAdapt,
+    kAfBadStart, kAfSubValid,
+    kAfCount = BGH_NUTS_ASYNC_N_FL
+};
+static_assert(kAfSubValid + 1 <= kAfCount, "async flag numbering");
+enum : int { kPhaseRun = 0, kPhaseFlush = 1, kPhaseFinished = 2 };
+enum : int {   // extra scalars of the async machine, appended to the lock-step ones
+    kScH = kScCount, kScFgW, kScBgW, kScFgUse, kScBgUse,
+    kAscCount = BGH_NUTS_ASYNC_N_SC
+};
+static_assert(kScBgUse + 1 <= kAscCount, "async scalar numbering");
+
+struct AsyncParams {
+    NutsParams n;        // n.sc has kAscCount rows, n.partials kAsyncPartials quantities per block
+    int* afl;            // [kAfCount][Cp]
+    void* trace;         // [draws][D][C] fp64 or fp32
+    double* stats;       // [tune+draws][BGH_NUTS_N_STATS][C]
+    int* n_finished;     // device scalar
+    int trace_f32;
+    int tune, draws;
+    int early_draws, early_depth, max_depth, window;
+};
+cudaError_t nuts_async_launch_pre(const AsyncParams& p, cudaStream_t s);
+cudaError_t nuts_async_launch_post(const AsyncParams& p, cudaStream_t s);
+cudaError_t nuts_async_launch_init(const AsyncParams& p, double step0, double initial_weight, cudaStream_t s);   // leap1, leap2, leaf scalar (plus the likelihood + finalize)
 
 }  // namespace bgh

@@ -15,7 +15,7 @@ import time
 import numpy as np
 
 from . import _lib
-from ._lib import (NUTS_MAX_DEPTH, NUTS_MAX_PARTIALS, NUTS_N_FL, NUTS_N_SC, NUTS_N_SLOTS, NUTS_N_STATS,
+from ._lib import (NUTS_ASYNC_N_FL, NUTS_ASYNC_N_SC, NUTS_ASYNC_PARTIALS, bgh_nuts_async_buffers, NUTS_MAX_DEPTH, NUTS_MAX_PARTIALS, NUTS_N_FL, NUTS_N_SC, NUTS_N_SLOTS, NUTS_N_STATS,
                    NUTS_SC_EPS, NUTS_SC_LOGP, NUTS_SLOT_BG_MEAN, NUTS_SLOT_BG_RAW, NUTS_SLOT_FG_MEAN,
                    NUTS_SLOT_FG_RAW, NUTS_SLOT_GRAD, NUTS_SLOT_Q, NUTS_SLOT_VAR, bgh_nuts_buffers, bgh_nuts_cfg,
                    check)
@@ -39,10 +39,12 @@ class NutsSampler:
         self.n_vec_blocks = int(self.L.bgh_nuts_vec_blocks(engine.ctx))
         self.state = torch.zeros((NUTS_N_SLOTS, D, Cp), dtype=f64, device=dev)
         self.ckpt = torch.zeros((2, NUTS_MAX_DEPTH, D, Cp), dtype=f64, device=dev)
-        self.sc = torch.zeros((NUTS_N_SC, Cp), dtype=f64, device=dev)
+        self.sc = torch.zeros((max(NUTS_N_SC, NUTS_ASYNC_N_SC), Cp), dtype=f64, device=dev)
+        self.afl = torch.zeros((NUTS_ASYNC_N_FL, Cp), dtype=torch.int32, device=dev)
         self.fl = torch.zeros((NUTS_N_FL, Cp), dtype=torch.int32, device=dev)
-        self.partials = torch.zeros((self.n_vec_blocks, NUTS_MAX_PARTIALS, Cp), dtype=f64, device=dev)
-        self.sums = torch.zeros((NUTS_MAX_PARTIALS, Cp), dtype=f64, device=dev)
+        nq = max(NUTS_MAX_PARTIALS, NUTS_ASYNC_PARTIALS)
+        self.partials = torch.zeros((self.n_vec_blocks, nq, Cp), dtype=f64, device=dev)
+        self.sums = torch.zeros((nq, Cp), dtype=f64, device=dev)
         self.logp_w = torch.zeros(Cp, dtype=f64, device=dev)
         self.stats = torch.zeros((NUTS_N_STATS, Cp), dtype=f64, device=dev)
         self.n_active_dev = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -131,8 +133,44 @@ class NutsSampler:
         check(self.L.bgh_nuts_stop_tuning(self.eng.ctx, ctypes.byref(self.buf), ctypes.byref(self.cfg), self._stream()),
               self.eng.ctx)
 
-    # ------------------------------------------------------------------ pm.sample
-    def sample(self, draws, tune, trace_dtype=None, progress=None):
+    # ------------------------------------------------------------------ pm.sample, asynchronous chains
+    def sample(self, draws, tune, trace_dtype=None, progress=None, poll_ticks=64):
+        """pm.sample(draws, tune=tune): the whole run on the device (bgh_nuts_run).  Every tick advances
+        every chain by one leapfrog; chains never wait for the deepest tree of the batch.  Returns the
+        same dict as :meth:`sample_lockstep` (``leapfrogs`` holds the per-draw mean tree size over chains)."""
+        t = self.t
+        eng = self.eng
+        C = eng.C
+        dt = trace_dtype or t.float64
+        if dt not in (t.float64, t.float32):
+            raise ValueError("trace dtype must be float64 or float32")
+        trace = t.empty((max(draws, 1), eng.D, C), dtype=dt, device=eng.device)
+        stats = t.zeros((tune + draws, NUTS_N_STATS, C), dtype=t.float64, device=eng.device)
+        ab = bgh_nuts_async_buffers()
+        ab.base = self.buf
+        ab.afl = self.afl.data_ptr()
+        ab.trace = trace.data_ptr()
+        ab.run_stats = stats.data_ptr()
+        ab.trace_f32 = int(dt == t.float32)
+        n_ticks = ctypes.c_int64(0)
+        t.cuda.synchronize(eng.device)
+        t0 = time.perf_counter()
+        check(self.L.bgh_nuts_run(eng.ctx, ctypes.byref(ab), ctypes.byref(self.cfg), int(tune), int(draws),
+                                  int(poll_ticks), self._stream(), ctypes.byref(n_ticks)), eng.ctx)
+        t.cuda.synchronize(eng.device)
+        total = time.perf_counter() - t0
+        if int(self.afl[21, :C].sum().item()) != 0:          # kAfBadStart
+            raise ValueError("Bad initial energy: the energy at the start of a transition was not finite")
+        st = stats.cpu().numpy()
+        tree = st[:, 2, :]                                   # leapfrogs per transition and chain
+        frac_tune = tree[:tune].sum() / max(tree.sum(), 1.0)
+        self.total_leapfrogs += int(n_ticks.value)
+        self.draw += tune + draws
+        return dict(trace=trace[:draws], stats=st, leapfrogs=tree.mean(axis=1), ticks=int(n_ticks.value),
+                    seconds_tune=total * frac_tune, seconds_draws=total * (1.0 - frac_tune), seconds_total=total, tune=tune)
+
+    # ------------------------------------------------------------------ pm.sample, lock-step chains
+    def sample_lockstep(self, draws, tune, trace_dtype=None, progress=None):
         """Runs tune + draws transitions; returns a dict with
         ``trace``  torch tensor [draws, D, C] on the device (positions in the unconstrained space),
         ``stats``  numpy float64 [tune + draws, 8, C] (STAT_NAMES), ``leapfrogs`` int64 [tune + draws],

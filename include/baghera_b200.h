@@ -184,6 +184,9 @@ int bgh_debug_plan(int64_t M, const int32_t* gid_sorted, int32_t G, int32_t n_ct
 #define BGH_NUTS_SC_LOGP 1
 #define BGH_NUTS_N_FL 11
 #define BGH_NUTS_N_STATS 8
+#define BGH_NUTS_ASYNC_N_FL 24
+#define BGH_NUTS_ASYNC_N_SC 24
+#define BGH_NUTS_ASYNC_PARTIALS (2 * BGH_NUTS_MAX_DEPTH + 4)
 
 typedef struct bgh_nuts_buffers {
     double* state;
@@ -229,6 +232,30 @@ int bgh_nuts_transition(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nut
 
 /* End of tuning: step size <- exp(log_step_bar) (DualAverageAdaptation.current(tune=False)). */
 int bgh_nuts_stop_tuning(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nuts_cfg* cfg, void* stream);
+
+/* ---- asynchronous batched NUTS: the whole pm.sample(draws, tune) run on the device --------------
+ * Every "tick" (one batched logp+grad evaluation) advances every chain by one leapfrog; a chain whose
+ * tree stops starts its next transition in the next tick, so no chain waits for the deepest tree of
+ * the batch.  Per-chain decisions depend only on the chain's own state and on Philox counters keyed by
+ * its own draw index, hence the result equals the lock-step bgh_nuts_transition loop.  One tick is
+ * captured in a CUDA graph; the host only polls the number of finished chains every `poll_ticks`.
+ * Buffers: as bgh_nuts_buffers, but sc has BGH_NUTS_ASYNC_N_SC rows and partials
+ * BGH_NUTS_ASYNC_PARTIALS quantities per block; plus
+ *   afl      int32[BGH_NUTS_ASYNC_N_FL][Cp]
+ *   trace    [draws][D][C] fp64 (trace_f32 = 0) or fp32: positions after each post-tuning transition
+ *   stats    double[tune + draws][BGH_NUTS_N_STATS][C]
+ * Call bgh_nuts_init first (start point, mass-matrix slots); then bgh_nuts_run once. */
+typedef struct bgh_nuts_async_buffers {
+    bgh_nuts_buffers base;
+    int32_t* afl;
+    void* trace;
+    double* run_stats;
+    int32_t trace_f32;
+    int32_t reserved;
+} bgh_nuts_async_buffers;
+
+int bgh_nuts_run(bgh_ctx* ctx, const bgh_nuts_async_buffers* buf, const bgh_nuts_cfg* cfg, int32_t tune,
+                 int32_t draws, int32_t poll_ticks, void* stream, int64_t* n_ticks);
 
 /* Tools only: per-warp phase timestamps (globaltimer ns) of the likelihood kernel.  enable != 0
  * allocates the trace buffer; out (optional) receives the last launch's

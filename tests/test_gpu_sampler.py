@@ -59,15 +59,15 @@ def test_sampler_is_reproducible_and_seed_sensitive():
     d, eng, s = _setup(3000, 10, 4, seed=5, data_seed=3)
     q0 = synth.jittered_start(13, 4, seed=1)
     s.init(q0)
-    a = s.sample(draws=20, tune=30)["trace"].cpu().numpy()
+    a = s.sample_lockstep(draws=20, tune=30)["trace"].cpu().numpy()
     from baghera_b200.sampler import NutsSampler
     s2 = NutsSampler(eng, seed=5)
     s2.init(q0)
-    b = s2.sample(draws=20, tune=30)["trace"].cpu().numpy()
+    b = s2.sample_lockstep(draws=20, tune=30)["trace"].cpu().numpy()
     assert np.array_equal(a, b)                          # counter-based RNG + fixed summation order
     s3 = NutsSampler(eng, seed=6)
     s3.init(q0)
-    c = s3.sample(draws=20, tune=30)["trace"].cpu().numpy()
+    c = s3.sample_lockstep(draws=20, tune=30)["trace"].cpu().numpy()
     assert not np.array_equal(a, c)
     eng.close()
 
@@ -105,4 +105,24 @@ def test_full_size_transitions():
     lp = s.logp.cpu().numpy()
     assert np.all(np.isfinite(lp)) and np.all(lp > lp0)   # chains climb from the jittered start
     assert np.all(np.isfinite(s.q.cpu().numpy()))
+    eng.close()
+
+
+def test_async_machine_reproduces_lockstep_chains():
+    """The asynchronous per-chain state machine makes the same decisions as the lock-step loop: with the
+    same seed both produce the same chains (Philox counters are keyed by each chain's own draw index)."""
+    from baghera_b200.sampler import NutsSampler
+    d, eng, s = _setup(3000, 10, 4, seed=5, data_seed=3)
+    q0 = synth.jittered_start(13, 4, seed=1)
+    s.init(q0)
+    a = s.sample_lockstep(draws=25, tune=40)
+    s2 = NutsSampler(eng, seed=5)
+    s2.init(q0)
+    b = s2.sample(draws=25, tune=40, poll_ticks=16)
+    ta, tb = a["trace"].cpu().numpy(), b["trace"].cpu().numpy()
+    assert np.array_equal(a["stats"][:, 0], b["stats"][:, 0])          # tree depths
+    assert np.array_equal(a["stats"][:, 2], b["stats"][:, 2])          # tree sizes
+    assert np.allclose(ta, tb, rtol=1e-12, atol=0)
+    # the async run needs far fewer batched evaluations than the lock-step one
+    assert b["ticks"] <= a["leapfrogs"].sum() + 65 * 16
     eng.close()
