@@ -974,10 +974,20 @@ int bgh_nuts_run(bgh_ctx* ctx, const bgh_nuts_async_buffers* buf, const bgh_nuts
     // a transition needs at most 2^10 - 1 leaves; bound the loop so that a logic error cannot hang the GPU
     const int64_t max_ticks = (int64_t)(tune + draws) * 1024 + 1024;
     int status = BGH_OK;
+    const char* no_graph_env = getenv("BGH_NUTS_NO_GRAPH");   // tuning / debugging only
+    const bool no_graph = no_graph_env && *no_graph_env == '1';
     while (ticks < max_ticks) {
         for (int i = 0; i < poll_ticks; ++i) {
-            cudaError_t e = cudaGraphLaunch(exec, s);
-            if (e != cudaSuccess) { status = fail(ctx, BGH_ECUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(e)); break; }
+            cudaError_t e;
+            if (no_graph) {
+                e = nuts_async_launch_pre(a, s);
+                if (e == cudaSuccess && run_local(ctx, qw, buf->base.logp_w, gw, ctx->d_payload, true, s) != BGH_OK) e = cudaErrorUnknown;
+                if (e == cudaSuccess) e = nuts_async_launch_post(a, s);
+                ctx->launches -= 2;
+            } else {
+                e = cudaGraphLaunch(exec, s);
+            }
+            if (e != cudaSuccess) { status = fail(ctx, BGH_ECUDA, std::string("tick launch: ") + cudaGetErrorString(e)); break; }
         }
         if (status != BGH_OK) break;
         ticks += poll_ticks;
