@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbaghera_b200.so")
+LIB_PATH = os.environ.get("BGH_LIB_PATH") or os.path.join(_HERE, "libbaghera_b200.so")   # override: kernel-variant experiments (tools/)
 CSRC = os.path.join(_HERE, "csrc")
 
 BGH_ABI_VERSION = 1

@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 
+#include "bgh_fused.h"
 #include "bgh_internal.h"
 #include "bgh_sampler.h"
 
@@ -267,8 +268,9 @@ struct bgh_ctx {
     double lik_const = 0.0;
     Plan plan;
     // device data
-    float* d_chi2 = nullptr;
-    float* d_ld = nullptr;
+    double* d_xs = nullptr;   // prepared fp64 SoA {s/sqrt(l), 1/sqrt(l), sqrt(l)} (see bgh_lik_device.cuh)
+    double* d_xw = nullptr;
+    double* d_xl = nullptr;
     int* d_gid = nullptr;
     int4* d_groups = nullptr;
     double* d_slots = nullptr;
@@ -280,6 +282,13 @@ struct bgh_ctx {
     int* d_split_ptr = nullptr;
     int* d_split_slots = nullptr;
     unsigned long long* d_trace = nullptr;   // tools only (bgh_debug_trace)
+    // cooperative kernels (bgh_fused.cu): grid barrier words, status flag, tick counter
+    unsigned long long* d_bar = nullptr;
+    unsigned long long bar_count = 0;        // arrivals so far == value of *d_bar once queued launches finish
+    int* d_status = nullptr;
+    int* d_ticks = nullptr;
+    int* h_poll = nullptr;                   // pinned: {n_finished, status, ticks}
+    bool fused = true;                       // BGH_UNFUSED=1 -> separate likelihood / finalize launches
     // host-entry staging (lazily allocated)
     static constexpr int kPipe = 2;
     double* d_q_cd[kPipe] = {nullptr, nullptr};
@@ -399,6 +408,18 @@ int bgh_create(bgh_ctx** out, const bgh_cfg* cfg)
     ctx->n_cta = ctx->sm_count;
     ctx->n_groups = ctx->n_cta * kLikWarps * (32 / ctx->CL);
     e = lik_configure();
+    if (e == cudaSuccess) e = fused_configure();
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_bar, 256);
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_bar, 0, 256);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_status, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_status, 0, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_ticks, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_ticks, 0, sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_poll, 4 * sizeof(int));
+    {
+        const char* uf = getenv("BGH_UNFUSED");
+        ctx->fused = !(uf && *uf == '1') && prop.cooperativeLaunch != 0 && ctx->n_cta <= prop.multiProcessorCount;
+    }
     if (e != cudaSuccess) {
         std::string m = std::string("bgh_create: kernel configuration failed: ") + cudaGetErrorString(e);
         delete ctx;
@@ -412,9 +433,11 @@ void bgh_destroy(bgh_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
-    cudaFree(ctx->d_chi2); cudaFree(ctx->d_ld); cudaFree(ctx->d_gid); cudaFree(ctx->d_groups);
+    cudaFree(ctx->d_xs); cudaFree(ctx->d_xw); cudaFree(ctx->d_xl); cudaFree(ctx->d_gid); cudaFree(ctx->d_groups);
     cudaFree(ctx->d_slots); cudaFree(ctx->d_part); cudaFree(ctx->d_payload); cudaFree(ctx->d_cc);
     cudaFree(ctx->d_trace);
+    cudaFree(ctx->d_bar); cudaFree(ctx->d_status); cudaFree(ctx->d_ticks);
+    if (ctx->h_poll) cudaFreeHost(ctx->h_poll);
     cudaFree(ctx->d_split_gene); cudaFree(ctx->d_split_row); cudaFree(ctx->d_split_ptr); cudaFree(ctx->d_split_slots);
     for (int i = 0; i < bgh_ctx::kPipe; ++i) {
         cudaFree(ctx->d_q_cd[i]); cudaFree(ctx->d_q_dc[i]); cudaFree(ctx->d_g_dc[i]); cudaFree(ctx->d_g_cd[i]);
@@ -552,7 +575,7 @@ int bgh_upload(bgh_ctx* ctx, const float* chi2, const float* ld, const int32_t* 
     if (rc != BGH_OK) return fail(ctx, rc, err);
 
     auto dfree = [](auto*& p) { cudaFree(p); p = nullptr; };
-    dfree(ctx->d_chi2); dfree(ctx->d_ld); dfree(ctx->d_gid); dfree(ctx->d_groups); dfree(ctx->d_slots);
+    dfree(ctx->d_xs); dfree(ctx->d_xw); dfree(ctx->d_xl); dfree(ctx->d_gid); dfree(ctx->d_groups); dfree(ctx->d_slots);
     dfree(ctx->d_part); dfree(ctx->d_payload); dfree(ctx->d_cc); dfree(ctx->d_split_gene); dfree(ctx->d_split_row);
     dfree(ctx->d_split_ptr); dfree(ctx->d_split_slots);
 
@@ -564,8 +587,9 @@ int bgh_upload(bgh_ctx* ctx, const float* chi2, const float* ld, const int32_t* 
     const size_t ns = P.split_gene.size();
     const size_t nsl = std::max<size_t>(P.split_slots.size(), 1);
 
-    BGH_CUDA(ctx, cudaMalloc(&ctx->d_chi2, sizeof(float) * (size_t)Mpad));
-    BGH_CUDA(ctx, cudaMalloc(&ctx->d_ld, sizeof(float) * (size_t)Mpad));
+    BGH_CUDA(ctx, cudaMalloc(&ctx->d_xs, sizeof(double) * (size_t)Mpad));
+    BGH_CUDA(ctx, cudaMalloc(&ctx->d_xw, sizeof(double) * (size_t)Mpad));
+    BGH_CUDA(ctx, cudaMalloc(&ctx->d_xl, sizeof(double) * (size_t)Mpad));
     BGH_CUDA(ctx, cudaMalloc(&ctx->d_gid, sizeof(int) * (size_t)Mpad));
     BGH_CUDA(ctx, cudaMalloc(&ctx->d_groups, sizeof(int4) * groups.size()));
     BGH_CUDA(ctx, cudaMalloc(&ctx->d_slots, sizeof(double) * (2 * (size_t)ctx->n_groups + ctx->n_cta) * ctx->Cp));
@@ -576,8 +600,18 @@ int bgh_upload(bgh_ctx* ctx, const float* chi2, const float* ld, const int32_t* 
     BGH_CUDA(ctx, cudaMalloc(&ctx->d_split_row, sizeof(int) * std::max<size_t>(ns, 1)));
     BGH_CUDA(ctx, cudaMalloc(&ctx->d_split_ptr, sizeof(int) * (ns + 1)));
     BGH_CUDA(ctx, cudaMalloc(&ctx->d_split_slots, sizeof(int) * nsl));
-    BGH_CUDA(ctx, cudaMemcpy(ctx->d_chi2, s_sorted.data(), sizeof(float) * (size_t)Mpad, cudaMemcpyHostToDevice));
-    BGH_CUDA(ctx, cudaMemcpy(ctx->d_ld, l_sorted.data(), sizeof(float) * (size_t)Mpad, cudaMemcpyHostToDevice));
+    {
+        // prepared fp64 SoA: rho = sp - e wp - (c beta) lp is the standardised residual (bgh_lik_device.cuh)
+        std::vector<double> prep((size_t)Mpad);
+        for (int which = 0; which < 3; ++which) {
+            for (int64_t j = 0; j < Mpad; ++j) {
+                const double l = (double)l_sorted[(size_t)j], sq = sqrt(l);
+                prep[(size_t)j] = which == 0 ? (double)s_sorted[(size_t)j] / sq : (which == 1 ? 1.0 / sq : sq);
+            }
+            double* dst = which == 0 ? ctx->d_xs : (which == 1 ? ctx->d_xw : ctx->d_xl);
+            BGH_CUDA(ctx, cudaMemcpy(dst, prep.data(), sizeof(double) * (size_t)Mpad, cudaMemcpyHostToDevice));
+        }
+    }
     BGH_CUDA(ctx, cudaMemcpy(ctx->d_gid, g_sorted.data(), sizeof(int) * (size_t)Mpad, cudaMemcpyHostToDevice));
     BGH_CUDA(ctx, cudaMemcpy(ctx->d_groups, groups.data(), sizeof(int4) * groups.size(), cudaMemcpyHostToDevice));
     BGH_CUDA(ctx, cudaMemset(ctx->d_slots, 0, sizeof(double) * (2 * (size_t)ctx->n_groups + ctx->n_cta) * ctx->Cp));
@@ -595,9 +629,9 @@ int bgh_upload(bgh_ctx* ctx, const float* chi2, const float* ld, const int32_t* 
 static void fill_params(bgh_ctx* ctx, const double* q, double* grad, double* logp, double* payload,
                         LikParams* lp, FinParams* fp)
 {
-    lp->chi2 = ctx->d_chi2; lp->ld = ctx->d_ld; lp->gid = ctx->d_gid; lp->groups = ctx->d_groups;
+    lp->sp = ctx->d_xs; lp->wp = ctx->d_xw; lp->lp = ctx->d_xl; lp->gid = ctx->d_gid; lp->groups = ctx->d_groups;
     lp->q = q; lp->grad = grad; lp->slots = ctx->d_slots; lp->part = ctx->d_part; lp->cc = ctx->d_cc; lp->trace = ctx->d_trace;
-    lp->Cp = ctx->Cp; lp->G = ctx->cfg.n_genes; lp->NG = ctx->n_groups; lp->model = ctx->cfg.model;
+    lp->Cp = ctx->Cp; lp->G = ctx->cfg.n_genes; lp->NG = ctx->n_groups; lp->n_cta = ctx->n_cta; lp->model = ctx->cfg.model;
     lp->fix = ctx->cfg.fix_intercept; lp->c = ctx->cfg.c;
     fp->q = q; fp->grad = grad; fp->logp = logp; fp->slots = ctx->d_slots; fp->part = ctx->d_part; fp->cc = ctx->d_cc;
     fp->payload = payload;
@@ -621,6 +655,20 @@ static int run_local(bgh_ctx* ctx, const double* q, double* logp, double* grad, 
         ev = &ctx->prof_ev[3 * ctx->prof_n];
         ctx->prof_n++;
         BGH_CUDA(ctx, cudaEventRecord(ev[0], s));
+    }
+    if (ctx->fused) {
+        // one cooperative launch: likelihood pass | grid barrier | finalize (bgh_fused.cu)
+        FusedParams f;
+        f.lik = lp; f.fin = fp; f.bar = ctx->d_bar; f.status = ctx->d_status; f.chain_blocks = ctx->chain_blocks;
+        f.bar_base = ctx->bar_count;
+        ctx->bar_count += (unsigned long long)ctx->n_cta;   // one grid barrier per launch
+        BGH_CUDA(ctx, launch_logp_grad_fused(f, ctx->CL, ctx->CPL, ctx->n_cta, s));
+        if (ev) {
+            BGH_CUDA(ctx, cudaEventRecord(ev[1], s));
+            BGH_CUDA(ctx, cudaEventRecord(ev[2], s));
+        }
+        ctx->launches += 1;
+        return BGH_OK;
     }
     BGH_CUDA(ctx, launch_lik(lp, ctx->CL, ctx->CPL, ctx->n_cta, ctx->chain_blocks, s));
     if (ev) BGH_CUDA(ctx, cudaEventRecord(ev[1], s));
@@ -931,7 +979,7 @@ int bgh_nuts_run(bgh_ctx* ctx, const bgh_nuts_async_buffers* buf, const bgh_nuts
     if (rc != BGH_OK) return rc;
     if (!buf->afl || (draws > 0 && !buf->trace) || tune < 0 || draws < 0 || tune + draws <= 0)
         return fail(ctx, BGH_EINVAL, "bgh_nuts_run: bad argument");
-    if (ctx->Cp > 170) return fail(ctx, BGH_EINVAL, "bgh_nuts_run: at most 128 chains per context (use several contexts / GPUs)");
+    if (ctx->Cp > kLikThreads) return fail(ctx, BGH_EINVAL, "bgh_nuts_run: at most 512 chains per context (use several contexts / GPUs)");
     if (poll_ticks <= 0) poll_ticks = 64;
     a.afl = buf->afl; a.trace = buf->trace; a.stats = buf->run_stats; a.n_finished = buf->base.n_active_dev;
     a.trace_f32 = buf->trace_f32; a.tune = tune; a.draws = draws;
@@ -952,53 +1000,48 @@ int bgh_nuts_run(bgh_ctx* ctx, const bgh_nuts_async_buffers* buf, const bgh_nuts
     BGH_CUDA(ctx, cudaMemcpyAsync(qw, buf->base.state + kSlotQP * vec, sizeof(double) * vec, cudaMemcpyDeviceToDevice, s));
     ctx->launches += 1;
 
-    // one tick = pre, likelihood, finalize, post, scalar: captured once, replayed
-    const bool was_profiling = ctx->profiling;
-    ctx->profiling = false;
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
-    BGH_CUDA(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
-    cudaError_t e1 = nuts_async_launch_pre(a, s);
-    int rc2 = run_local(ctx, qw, buf->base.logp_w, gw, ctx->d_payload, true, s);
-    cudaError_t e2 = nuts_async_launch_post(a, s);
-    cudaError_t e3 = cudaStreamEndCapture(s, &graph);
-    ctx->launches -= 2;   // the capture itself launched nothing
-    ctx->profiling = was_profiling;
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || rc2 != BGH_OK || !graph) {
-        if (graph) cudaGraphDestroy(graph);
-        return fail(ctx, BGH_ECUDA, std::string("bgh_nuts_run: graph capture failed: ") +
-                                        cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
-    }
-    BGH_CUDA(ctx, cudaGraphInstantiate(&exec, graph, 0));
-    int64_t ticks = 0;
     // a transition needs at most 2^10 - 1 leaves; bound the loop so that a logic error cannot hang the GPU
     const int64_t max_ticks = (int64_t)(tune + draws) * 1024 + 1024;
+    int64_t ticks = 0;
     int status = BGH_OK;
-    const char* no_graph_env = getenv("BGH_NUTS_NO_GRAPH");   // tuning / debugging only
-    const bool no_graph = no_graph_env && *no_graph_env == '1';
+    if (!ctx->fused) return fail(ctx, BGH_ESTATE, "bgh_nuts_run: needs the cooperative kernels (BGH_UNFUSED is set or the device cannot co-schedule the grid)");
+    // persistent tick kernel (bgh_fused.cu): pre | likelihood | finalize | post | scalar per tick, grid
+    // barriers in between; one cooperative launch runs up to `poll_ticks` ticks, then the host polls
+    TickParams t;
+    fill_params(ctx, qw, gw, buf->base.logp_w, ctx->d_payload, &t.f.lik, &t.f.fin);
+    t.f.fin.finish_inline = 1;
+    t.f.lik.trace = nullptr;
+    t.f.bar = ctx->d_bar; t.f.status = ctx->d_status; t.f.chain_blocks = ctx->chain_blocks;
+    t.a = a;
+    t.a.n.n_vec_blocks = ctx->n_cta;
+    t.n_ticks = poll_ticks;
+    t.ticks_done = ctx->d_ticks;
+    t.phase_trace = ctx->d_trace;   // NULL unless bgh_debug_trace enabled it (tools/trace_ticks.py)
+    { const char* tf = getenv("BGH_TRACE_TICK"); t.trace_first = tf ? atoi(tf) : 0; }
+    t.tick_base = 0;
+    BGH_CUDA(ctx, cudaMemsetAsync(ctx->d_ticks, 0, sizeof(int), s));
     while (ticks < max_ticks) {
-        for (int i = 0; i < poll_ticks; ++i) {
-            cudaError_t e;
-            if (no_graph) {
-                e = nuts_async_launch_pre(a, s);
-                if (e == cudaSuccess && run_local(ctx, qw, buf->base.logp_w, gw, ctx->d_payload, true, s) != BGH_OK) e = cudaErrorUnknown;
-                if (e == cudaSuccess) e = nuts_async_launch_post(a, s);
-                ctx->launches -= 2;
-            } else {
-                e = cudaGraphLaunch(exec, s);
-            }
-            if (e != cudaSuccess) { status = fail(ctx, BGH_ECUDA, std::string("tick launch: ") + cudaGetErrorString(e)); break; }
-        }
-        if (status != BGH_OK) break;
-        ticks += poll_ticks;
-        ctx->launches += 5 * (int64_t)poll_ticks;
-        cudaError_t e = cudaMemcpyAsync(buf->base.n_active_host, buf->base.n_active_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+        t.f.bar_base = ctx->bar_count;
+        cudaError_t e = launch_nuts_ticks(t, ctx->CL, ctx->CPL, ctx->n_cta, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&ctx->h_poll[0], buf->base.n_active_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&ctx->h_poll[1], ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&ctx->h_poll[2], ctx->d_ticks, sizeof(int), cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) { status = fail(ctx, BGH_ECUDA, std::string("bgh_nuts_run: ") + cudaGetErrorString(e)); break; }
-        if (*buf->base.n_active_host >= ctx->cfg.n_chains) break;
+        ctx->launches += 1;
+        ctx->bar_count += 5ull * (unsigned long long)ctx->n_cta * (unsigned long long)(ctx->h_poll[2] - ticks);
+        ticks = ctx->h_poll[2];
+        t.tick_base = (int)ticks;
+        if (ctx->h_poll[1] != 0) {
+            cudaMemset(ctx->d_bar, 0, 256);
+            cudaMemset(ctx->d_status, 0, sizeof(int));
+            ctx->bar_count = 0;
+            status = fail(ctx, BGH_ECUDA, "bgh_nuts_run: grid barrier timed out inside the tick kernel");
+            break;
+        }
+        *buf->base.n_active_host = ctx->h_poll[0];
+        if (ctx->h_poll[0] >= ctx->cfg.n_chains) break;
     }
-    cudaGraphExecDestroy(exec);
-    cudaGraphDestroy(graph);
     if (status == BGH_OK && ticks >= max_ticks) status = fail(ctx, BGH_ESTATE, "bgh_nuts_run: tick budget exhausted");
     if (n_ticks) *n_ticks = ticks;
     return status;

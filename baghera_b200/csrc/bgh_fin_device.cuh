@@ -1,0 +1,122 @@
+// bgh_fin_device.cuh — per-chain closing formulas (priors, transforms, Jacobians) shared by the
+// stand-alone finalize / finish kernels (bgh_lik.cu) and the fused kernels (bgh_fused.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "bgh_internal.h"
+#include "bgh_lik_device.cuh"
+
+namespace bgh {
+
+// ---------------------------------------------------------------------------------------------
+// per-chain closing formulas (priors, transforms, Jacobians) — ref: gene_regression.py:78-81,
+// heritability.py:45-49; PyMC3 3.6 distributions/continuous.py + transforms.py
+// ---------------------------------------------------------------------------------------------
+struct ChainSums {
+    double A_ll, A_e, S1, S2;
+};
+// Sum-independent per-chain terms of the closing formulas: computed once per evaluation, in
+// parallel with the partial-sum reduction (finalize) or directly (finish kernel).
+//   gene model: {iW, iW2, mi, lp0}   lp0 = all logp terms that do not involve the four sums
+//   gw model  : {sg0 (sigmoid of x0 when the intercept is "fixed"), -, mi, lp0}
+struct ChainConst {
+    double iW, iW2, mi, lp0;
+};
+
+__device__ __forceinline__ ChainConst chain_const(const FinParams& p, int ch)
+{
+    const int Cp = p.Cp;
+    ChainConst c;
+    if (p.model == BGH_MODEL_GENE_NORMAL) {
+        const double xW = p.q[0 * Cp + ch], e = p.q[1 * Cp + ch], xm = p.q[2 * Cp + ch];
+        const double ax = fabs(xm);
+        const double u = exp(-ax);                 // one exp + one log1p serve sigmoid and both logs
+        const double L = log1p(u);
+        c.iW = exp(-xW);
+        c.iW2 = c.iW * c.iW;
+        c.mi = (xm >= 0.0 ? 1.0 : u) / (1.0 + u);
+        const double G = (double)p.G_total;
+        // log sigmoid(x) + log(1 - sigmoid(x)) = -|x| - 2 log1p(exp(-|x|))
+        double lp = (-c.iW - 2.0 * xW) + xW;                       // InverseGamma(1,1) + log-Jacobian
+        lp += -0.5 * (e - 1.0) * (e - 1.0) - 0.5 * kLog2Pi;        // Normal(1,1)
+        lp += -ax - 2.0 * L;                                       // Beta(1,1)=0 ; logodds Jacobian
+        lp += -G * xW - 0.5 * G * kLog2Pi;                         // Normal(beta | mi, W) constants
+        lp += p.lik_const;
+        c.lp0 = lp;
+    } else {
+        const double x0 = p.q[0 * Cp + ch], xm = p.q[1 * Cp + ch];
+        const double ax = fabs(xm);
+        const double u = exp(-ax);
+        const double L = log1p(u);
+        c.mi = (xm >= 0.0 ? 1.0 : u) / (1.0 + u);
+        const double l1m = (xm >= 0.0 ? -xm : 0.0) - L;            // log(1 - mi)
+        double lp = l1m + 0.69314718055994530942;                  // Beta(1,2)
+        lp += -ax - 2.0 * L;                                       // logodds Jacobian
+        c.iW = 0.0;
+        if (p.fix) {
+            // Uniform(lo,hi) logp = -log(hi-lo); interval Jacobian = log(hi-lo) + log sigmoid'(x0)
+            const double a0 = fabs(x0), u0 = exp(-a0);
+            c.iW = (x0 >= 0.0 ? 1.0 : u0) / (1.0 + u0);            // sigmoid(x0)
+            lp += -a0 - 2.0 * log1p(u0);
+        } else {
+            lp += -0.5 * (x0 - 1.0) * (x0 - 1.0) - 0.5 * kLog2Pi;
+        }
+        lp += p.lik_const;
+        c.iW2 = 0.0;
+        c.lp0 = lp;
+    }
+    return c;
+}
+
+__device__ __forceinline__ void finish_chain(const FinParams& p, int ch, const ChainSums& s, const ChainConst& c)
+{
+    const int Cp = p.Cp;
+    if (p.model == BGH_MODEL_GENE_NORMAL) {
+        const double e = p.q[1 * Cp + ch];
+        const double G = (double)p.G_total;
+        p.logp[ch] = c.lp0 - 0.5 * s.S2 * c.iW2 - 0.5 * s.A_ll;
+        p.grad[0 * Cp + ch] = c.iW - 1.0 + s.S2 * c.iW2 - G;
+        p.grad[1 * Cp + ch] = -(e - 1.0) + (p.fix ? 0.0 : s.A_e);
+        p.grad[2 * Cp + ch] = 1.0 - 2.0 * c.mi + c.mi * (1.0 - c.mi) * s.S1 * c.iW2;
+    } else {
+        const double x0 = p.q[0 * Cp + ch];
+        p.logp[ch] = c.lp0 - 0.5 * s.A_ll;
+        if (p.fix) {
+            const double sg = c.iW;
+            p.grad[0 * Cp + ch] = s.A_e * (kGwFixHi - kGwFixLo) * sg * (1.0 - sg) + (1.0 - 2.0 * sg);
+        } else {
+            p.grad[0 * Cp + ch] = -(x0 - 1.0) + s.A_e;
+        }
+    }
+}
+
+// gradient row of a gene from its total residual sum.  The per-chain constants (1/W^2, mi) were
+// computed by the likelihood kernel and left in p.cc, so no exp() chain sits on this path.
+struct GeneCoef {
+    double iW2, mi, beta;
+};
+__device__ __forceinline__ GeneCoef load_gene_coef(const FinParams& p, int gene, int ch, bool needed)
+{
+    GeneCoef gc;
+    gc.iW2 = gc.mi = gc.beta = 0.0;
+    if (needed) {
+        gc.iW2 = p.cc[0 * p.Cp + ch];
+        gc.mi = p.cc[1 * p.Cp + ch];
+        if (p.model == BGH_MODEL_GENE_NORMAL) gc.beta = p.q[(size_t)(3 + gene) * p.Cp + ch];
+    }
+    return gc;
+}
+__device__ __forceinline__ void finish_gene(const FinParams& p, int gene, int ch, double sum_r, const GeneCoef& gc)
+{
+    const int Cp = p.Cp;
+    if (p.model == BGH_MODEL_GENE_NORMAL) {
+        p.grad[(size_t)(3 + gene) * Cp + ch] = fma(p.c, sum_r, -(gc.beta - gc.mi) * gc.iW2);
+    } else {
+        // (c*sum_r - 1/(1-mi)) * mi(1-mi) + (1 - 2mi)
+        p.grad[1 * Cp + ch] = p.c * sum_r * gc.mi * (1.0 - gc.mi) + 1.0 - 3.0 * gc.mi;
+    }
+}
+
+}  // namespace bgh

@@ -52,8 +52,9 @@ int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_cta, int groups_p
                Plan* plan, std::string* err);
 
 struct LikParams {
-    const float* chi2;
-    const float* ld;
+    const double* sp;     // prepared SoA, gene sorted: s / sqrt(l)
+    const double* wp;     //                            1 / sqrt(l)
+    const double* lp;     //                            sqrt(l)
     const int* gid;
     const int4* groups;   // {a, b, flags, gene id of SNP a}
     const double* q;      // [D][Cp]
@@ -65,6 +66,7 @@ struct LikParams {
     int Cp;
     int G;
     int NG;
+    int n_cta;
     int model;
     int fix;
     double c;

@@ -4,58 +4,33 @@
 // (gather beta[cat] -> Elemwise{Composite} -> Sum -> AdvancedIncSubtensor1 scatter-add)
 // and ref: baghera_tool/heritability.py:44-55 (genome-wide model) with one streaming pass.
 //
-// Mapping (sm_100a, no tensor cores: the work is FP64-pipe / HBM bound, not a contraction):
-//   * SNPs are sorted by gene on upload.  A *group* of CL lanes owns one contiguous SNP range and
-//     walks it sequentially; each lane of the group carries CPL chains.  Because every lane of a
-//     group sees the same SNP, a gene boundary is group-uniform: the per-gene residual sum is a
-//     plain sequential fp64 accumulation that is flushed with one coalesced store when the gene id
-//     changes — the "segmented reduction" needs no shuffles and no atomics and is bit-reproducible.
-//   * the SoA (chi2 fp32, ld fp32, gene_id int32) stream is read with 128-bit non-allocating loads,
-//     converted once per warp (fp32->fp64, w = 1/l) and staged in warp-private shared memory, from
-//     which all lanes broadcast-read it (2 x LDS.128 per SNP) — the conversion cost is amortised
-//     over CL*CPL chains.  The next chunk's global loads are in flight while the current one is
-//     being consumed (register double-buffering).
-//   * per (SNP, chain) the inner loop is 6 FP64 instructions:
-//         d = s - e;  r = fma(-l, c*beta, d);  acc_g += r;  t = r*w;  acc_e += t;  acc_ll = fma(r, t, acc_ll)
-//   * ranges that start or end inside a gene (NonCoding spans ~45% of all SNPs) write "slot"
-//     partials; bgh_finalize sums the slots of each such gene in a fixed order.
+// The device code of K1 (mapping, staging, inner loop) is documented in bgh_lik_device.cuh; this
+// file holds the stand-alone kernels (likelihood, finalize, finish, layout transposes) and launchers.
 #include <cuda_runtime.h>
 #include <math.h>
 
 #include "bgh_internal.h"
+#include "bgh_lik_device.cuh"
+#include "bgh_fin_device.cuh"
 
 namespace bgh {
 
 // ---------------------------------------------------------------------------------------------
-// small device helpers
+// K1 stand-alone: one CTA per (likelihood CTA, chain block).  The device code lives in
+// bgh_lik_device.cuh (shared with the fused / persistent kernels).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 ldg_stream_f4(const float* p)
+size_t lik_smem_bytes() { return kLikSmemBytes; }
+
+template <int CL, int CPL>
+__global__ void __launch_bounds__(kLikThreads, 1) lik_kernel(const LikParams p)
 {
-    float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-                 : "l"(p));
-    return r;
-}
-__device__ __forceinline__ int4 ldg_stream_i4(const int* p)
-{
-    int4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    lik_stage_init(smem_raw);
+    __syncthreads();
+    uint32_t par = 0;
+    lik_phase<CL, CPL>(p, smem_raw, blockIdx.x, blockIdx.y, par);
 }
 
-__device__ __forceinline__ double sigmoid_d(double x)
-{
-    // stable for both signs
-    if (x >= 0.0) {
-        const double z = exp(-x);
-        return 1.0 / (1.0 + z);
-    }
-    const double z = exp(x);
-    return z / (1.0 + z);
-}
 // log(sigmoid(x)) and log(1 - sigmoid(x)) without cancellation
 __device__ __forceinline__ double log_sigmoid_d(double x)
 {
@@ -64,483 +39,6 @@ __device__ __forceinline__ double log_sigmoid_d(double x)
 __device__ __forceinline__ double log1m_sigmoid_d(double x)
 {
     return x >= 0.0 ? -x - log1p(exp(-x)) : -log1p(exp(x));
-}
-
-// gw model with a "fixed" intercept: e = Uniform(0.9999, 1.0000001), interval-transformed
-// (ref: baghera_tool/heritability.py:45-46)
-constexpr double kGwFixLo = 0.9999;
-constexpr double kGwFixHi = 1.0000001;
-
-// Warp-private staging area, structure of arrays: s[kStride] (chi2), nl[kStride] (-ld), w[kStride]
-// (1/ld) as fp64 and g[kStride] (gene id).  Group grp of a warp owns elements [grp*(CH+2), +CH): the
-// +2 doubles of padding shift consecutive groups by 16 bytes so that the per-group broadcast
-// LDS.128 of the SL groups fall into different banks.
-constexpr int kStride = kChunk + 2 * 8;    // fp64 arrays: up to 8 groups per warp, +2 doubles each
-constexpr int kStrideG = kChunk + 4 * 8;   // gene ids: +4 ints per group keeps the int4 stores aligned
-constexpr size_t kWarpStageBytes = (size_t)kStride * 3 * sizeof(double) + (size_t)kStrideG * sizeof(int);
-static_assert(kWarpStageBytes % 16 == 0, "warp staging area must keep 16-byte alignment");
-
-size_t lik_smem_bytes()
-{
-    const size_t stage = (size_t)kLikWarps * kWarpStageBytes;
-    const size_t red = (size_t)kLikWarps * 5 * 64 * sizeof(double);   // epilogue reduction reuses the area
-    return stage > red ? stage : red;
-}
-
-// ---------------------------------------------------------------------------------------------
-// K1: fused likelihood + gradient
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long global_timer_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-__device__ __forceinline__ unsigned sm_id()
-{
-    unsigned r;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
-    return r;
-}
-// optional per-warp phase timestamps (tools/trace_lik.py); p.trace is NULL in production
-#define BGH_TRACE(slot)                                                                          \
-    do {                                                                                         \
-        if (p.trace != nullptr && lane == 0)                                                     \
-            p.trace[((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * kLikWarps + warp) * 8 + (slot)] = global_timer_ns(); \
-    } while (0)
-
-template <int CL, int CPL>
-__global__ void __launch_bounds__(kLikThreads, 1) lik_kernel(const LikParams p)
-{
-    constexpr int SL = 32 / CL;     // groups per warp
-    constexpr int CH = 4 * CL;      // SNPs per group per chunk (SL * CH == kChunk)
-    constexpr int CG = CL * CPL;    // chains per chain block
-    constexpr int B = kLikBatch;    // SNPs per branch-free batch
-    static_assert(SL * CH == kChunk, "chunk geometry");
-    static_assert(CH % B == 0, "batch must divide the chunk");
-
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int grp = lane / CL;
-    const int lc = lane % CL;
-    const unsigned gmask = (CL == 32) ? 0xffffffffu : (((1u << CL) - 1u) << (grp * CL));
-    const int v = (blockIdx.x * kLikWarps + warp) * SL + grp;
-    const int Cp = p.Cp;
-    const int ch0 = blockIdx.y * CG + lc;   // chain of slot k is ch0 + k*CL
-    const bool gene_model = p.model == BGH_MODEL_GENE_NORMAL;
-
-    // SNP i (0 <= i < CH) of this group lives at index i of the group's slice of each array
-    double* const sm_s = reinterpret_cast<double*>(smem_raw + (size_t)warp * kWarpStageBytes) + grp * (CH + 2);
-    double* const sm_nl = sm_s + kStride;
-    double* const sm_w = sm_nl + kStride;
-    int* const sm_g = reinterpret_cast<int*>(reinterpret_cast<double*>(smem_raw + (size_t)warp * kWarpStageBytes) + 3 * kStride) + grp * (CH + 4);
-    BGH_TRACE(0);
-    if (p.trace != nullptr && lane == 0)
-        p.trace[((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * kLikWarps + warp) * 8 + 7] = sm_id();
-
-    // ---- group descriptor, then get the first loads in flight before the exp() preamble --------
-    const int4 desc = p.groups[v];
-    const int ra = desc.x, rb = desc.y, flags = desc.z, g_first = desc.w;
-    const bool exclusive = (flags & kExclusive) != 0;
-    const bool active = ra < rb;
-    const double* const beta = p.q + (size_t)3 * Cp + ch0;   // gene model rows 3.. (this lane's chains)
-
-    int base = ra & ~(CH - 1);   // CH aligned so every lane's 4-vector is 16-byte aligned
-    float4 rs = make_float4(0.f, 0.f, 0.f, 0.f), rl = make_float4(1.f, 1.f, 1.f, 1.f);
-    int4 rg = make_int4(0, 0, 0, 0);
-    double braw[CPL], bn[CPL];
-#pragma unroll
-    for (int k = 0; k < CPL; ++k) braw[k] = bn[k] = 0.0;
-    if (active) {
-        rs = ldg_stream_f4(p.chi2 + base + lc * 4);
-        rl = ldg_stream_f4(p.ld + base + lc * 4);
-        rg = ldg_stream_i4(p.gid + base + lc * 4);
-        if (gene_model) {
-#pragma unroll
-            for (int k = 0; k < CPL; ++k) {
-                braw[k] = beta[(size_t)g_first * Cp + k * CL];
-                bn[k] = (g_first + 1 < p.G) ? beta[(size_t)(g_first + 1) * Cp + k * CL] : 0.0;
-            }
-        }
-    }
-
-    // ---- per-chain constants ----------------------------------------------------------------
-    double e[CPL], mi[CPL], iW2[CPL];
-#pragma unroll
-    for (int k = 0; k < CPL; ++k) {
-        const int ch = ch0 + k * CL;
-        if (gene_model) {
-            const double xW = p.q[0 * Cp + ch];
-            const double ev = p.q[1 * Cp + ch];
-            const double xm = p.q[2 * Cp + ch];
-            iW2[k] = exp(-2.0 * xW);
-            mi[k] = sigmoid_d(xm);
-            e[k] = p.fix ? 1.0 : ev;                 // ref: gene_regression.py:85-90
-        } else {
-            const double x0 = p.q[0 * Cp + ch];
-            const double xm = p.q[1 * Cp + ch];
-            iW2[k] = 0.0;
-            mi[k] = sigmoid_d(xm);
-            e[k] = p.fix ? (kGwFixLo + (kGwFixHi - kGwFixLo) * sigmoid_d(x0)) : x0;
-            braw[k] = bn[k] = mi[k];                 // the single slope of heritability.py:50-55
-        }
-    }
-
-    if (blockIdx.x == 0 && warp == 0 && grp == 0) {   // hand the per-chain constants to finalize
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) {
-            p.cc[0 * Cp + ch0 + k * CL] = iW2[k];
-            p.cc[1 * Cp + ch0 + k * CL] = mi[k];
-        }
-    }
-
-    double b[CPL], db[CPL];
-    double ag[CPL], ae[CPL], al[CPL], s1[CPL], s2[CPL], ax[CPL];
-#pragma unroll
-    for (int k = 0; k < CPL; ++k) {
-        b[k] = p.c * braw[k];
-        db[k] = braw[k] - mi[k];
-        ag[k] = ae[k] = al[k] = s1[k] = s2[k] = ax[k] = 0.0;
-    }
-
-    BGH_TRACE(1);
-    if (active) {
-        const bool head_partial = (flags & kHeadPartial) != 0;
-        const bool tail_partial = (flags & kTailPartial) != 0;
-        int cur = g_first;
-
-        auto load_beta = [&](int g, double (&dst)[CPL]) {
-#pragma unroll
-            for (int k = 0; k < CPL; ++k) {
-                if (gene_model)
-                    dst[k] = (g < p.G) ? beta[(size_t)g * Cp + k * CL] : 0.0;
-                else
-                    dst[k] = mi[k];
-            }
-        };
-        // gene `cur` is complete within this range (or the range ends): emit its sum
-        auto flush = [&](bool final_flush) {
-            bool owner;
-            if (exclusive) {
-                // every group of this CTA accumulates the same gene: reduced in the CTA epilogue
-#pragma unroll
-                for (int k = 0; k < CPL; ++k) ax[k] = ag[k];
-                owner = (flags & kOwner) != 0;
-            } else {
-                const bool to_head = (cur == g_first) && head_partial;
-                const bool to_tail = !to_head && final_flush && tail_partial;
-                if (to_head || to_tail) {
-                    double* dst = p.slots + (size_t)(to_head ? v : p.NG + v) * Cp + ch0;
-#pragma unroll
-                    for (int k = 0; k < CPL; ++k) dst[k * CL] = ag[k];
-                } else if (gene_model) {
-                    double* dst = p.grad + (size_t)(3 + cur) * Cp + ch0;
-#pragma unroll
-                    for (int k = 0; k < CPL; ++k) dst[k * CL] = fma(p.c, ag[k], -db[k] * iW2[k]);
-                }
-                owner = !to_head;   // this group holds the gene's first SNP: it owns the prior terms
-            }
-            if (owner) {
-#pragma unroll
-                for (int k = 0; k < CPL; ++k) {
-                    s1[k] += db[k];
-                    s2[k] = fma(db[k], db[k], s2[k]);
-                }
-            }
-        };
-        // switch to gene g (its raw beta in src), prefetch the row after it
-        auto enter_gene = [&](int g, const double (&src)[CPL]) {
-#pragma unroll
-            for (int k = 0; k < CPL; ++k) {
-                b[k] = p.c * src[k];
-                db[k] = src[k] - mi[k];
-            }
-            cur = g;
-            load_beta(g + 1, bn);   // genes are consecutive after the sort
-        };
-        auto accumulate = [&](const double sv, const double nlv, const double w) {
-#pragma unroll
-            for (int k = 0; k < CPL; ++k) {
-                const double d = sv - e[k];
-                const double r = fma(nlv, b[k], d);
-                ag[k] += r;
-                const double t = r * w;
-                ae[k] += t;
-                al[k] = fma(r, t, al[k]);
-            }
-        };
-        // one SNP with the gene-boundary check (tail of a chunk / several boundaries in a batch)
-        auto step_checked = [&](int i) {
-            const int g_i = sm_g[i];
-            if (g_i != cur) {
-                flush(false);
-#pragma unroll
-                for (int k = 0; k < CPL; ++k) ag[k] = 0.0;
-                if (g_i == cur + 1) {
-                    double tmp[CPL];
-#pragma unroll
-                    for (int k = 0; k < CPL; ++k) tmp[k] = bn[k];
-                    enter_gene(g_i, tmp);
-                } else {
-                    double tmp[CPL];
-                    load_beta(g_i, tmp);
-                    enter_gene(g_i, tmp);
-                }
-            }
-            accumulate(sm_s[i], sm_nl[i], sm_w[i]);
-        };
-
-        for (; base < rb; base += CH) {
-            // convert + stage: this lane's 4 consecutive SNPs -> 2 x STS.128 per fp64 array
-            {
-                const double l0 = (double)rl.x, l1 = (double)rl.y, l2 = (double)rl.z, l3 = (double)rl.w;
-                double2* const ps = reinterpret_cast<double2*>(sm_s + lc * 4);
-                double2* const pn = reinterpret_cast<double2*>(sm_nl + lc * 4);
-                double2* const pw = reinterpret_cast<double2*>(sm_w + lc * 4);
-                ps[0] = make_double2((double)rs.x, (double)rs.y);
-                ps[1] = make_double2((double)rs.z, (double)rs.w);
-                pn[0] = make_double2(-l0, -l1);
-                pn[1] = make_double2(-l2, -l3);
-                pw[0] = make_double2(__drcp_rn(l0), __drcp_rn(l1));
-                pw[1] = make_double2(__drcp_rn(l2), __drcp_rn(l3));
-                *reinterpret_cast<int4*>(sm_g + lc * 4) = rg;
-            }
-            __syncwarp(gmask);
-            if (base + CH < rb) {
-                rs = ldg_stream_f4(p.chi2 + base + CH + lc * 4);
-                rl = ldg_stream_f4(p.ld + base + CH + lc * 4);
-                rg = ldg_stream_i4(p.gid + base + CH + lc * 4);
-            }
-            int i = max(ra - base, 0);
-            const int i1 = min(rb - base, CH);
-            // batches are B aligned (vector LDS); a range that starts mid-batch steps up to the boundary
-            for (; i < i1 && (i & (B - 1)) != 0; ++i) step_checked(i);
-            while (i + B <= i1) {
-                // SNPs are gene sorted: if the last SNP of the batch is still in `cur`, all of it is
-                const int g_last = sm_g[i + B - 1];
-                if (g_last == cur) {
-                    double2 s2v[B / 2], n2v[B / 2], w2v[B / 2];
-#pragma unroll
-                    for (int t = 0; t < B / 2; ++t) {
-                        s2v[t] = *reinterpret_cast<const double2*>(sm_s + i + 2 * t);
-                        n2v[t] = *reinterpret_cast<const double2*>(sm_nl + i + 2 * t);
-                        w2v[t] = *reinterpret_cast<const double2*>(sm_w + i + 2 * t);
-                    }
-#pragma unroll
-                    for (int t = 0; t < B / 2; ++t) {
-                        accumulate(s2v[t].x, n2v[t].x, w2v[t].x);
-                        accumulate(s2v[t].y, n2v[t].y, w2v[t].y);
-                    }
-                    i += B;
-                    continue;
-                }
-                // at least one gene boundary inside the batch: nlead SNPs still belong to `cur`
-                int nlead = 0;
-#pragma unroll
-                for (int t = 0; t < B - 1; ++t) nlead += (sm_g[i + t] == cur) ? 1 : 0;
-                if (sm_g[i + nlead] == g_last) {
-                    // exactly one boundary: [0,nlead) -> cur, [nlead,B) -> g_last. The two per-chain
-                    // sums that do not depend on the gene (ae, al) run straight through; only the
-                    // slope and the per-gene accumulator are selected per SNP.
-                    double raw2[CPL], b2[CPL], ag2[CPL];
-                    if (g_last == cur + 1) {
-#pragma unroll
-                        for (int k = 0; k < CPL; ++k) raw2[k] = bn[k];
-                    } else {
-                        load_beta(g_last, raw2);
-                    }
-#pragma unroll
-                    for (int k = 0; k < CPL; ++k) {
-                        b2[k] = p.c * raw2[k];
-                        ag2[k] = 0.0;
-                    }
-#pragma unroll
-                    for (int t = 0; t < B; ++t) {
-                        const double sv = sm_s[i + t], nlv = sm_nl[i + t];
-                        const double w = sm_w[i + t];
-                        const bool lead = t < nlead;
-#pragma unroll
-                        for (int k = 0; k < CPL; ++k) {
-                            const double d = sv - e[k];
-                            const double r = fma(nlv, lead ? b[k] : b2[k], d);
-                            if (lead) ag[k] += r; else ag2[k] += r;
-                            const double tt = r * w;
-                            ae[k] += tt;
-                            al[k] = fma(r, tt, al[k]);
-                        }
-                    }
-                    flush(false);
-#pragma unroll
-                    for (int k = 0; k < CPL; ++k) ag[k] = ag2[k];
-                    enter_gene(g_last, raw2);
-                    i += B;
-                } else {
-                    // several boundaries (genes shorter than a batch): step through the whole batch so
-                    // that the next one stays B aligned
-                    for (int t = 0; t < B; ++t) step_checked(i + t);
-                    i += B;
-                }
-            }
-            for (; i < i1; ++i) step_checked(i);
-            __syncwarp(gmask);
-        }
-        flush(true);
-    }
-
-    BGH_TRACE(2);
-    // ---- CTA reduction of the per-chain scalars (fixed order -> deterministic) ---------------
-    // 1) across the SL groups of a warp (same lc): xor-shuffle tree
-#pragma unroll
-    for (int o = CL; o < 32; o <<= 1) {
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) {
-            al[k] += __shfl_xor_sync(0xffffffffu, al[k], o);
-            ae[k] += __shfl_xor_sync(0xffffffffu, ae[k], o);
-            s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], o);
-            s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], o);
-            ax[k] += __shfl_xor_sync(0xffffffffu, ax[k], o);
-        }
-    }
-    // 2) across warps through shared memory (reuses the staging area)
-    __syncthreads();
-    BGH_TRACE(3);
-    double* const red = reinterpret_cast<double*>(smem_raw);   // [kLikWarps][5][CG]
-    if (grp == 0) {
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) {
-            const int cc = lc + k * CL;
-            red[(warp * 5 + 0) * CG + cc] = al[k];
-            red[(warp * 5 + 1) * CG + cc] = ae[k];
-            red[(warp * 5 + 2) * CG + cc] = s1[k];
-            red[(warp * 5 + 3) * CG + cc] = s2[k];
-            red[(warp * 5 + 4) * CG + cc] = ax[k];
-        }
-    }
-    __syncthreads();
-    const bool cta_exclusive = (p.groups[blockIdx.x * kLikWarps * SL].z & kExclusive) != 0;
-    for (int o = threadIdx.x; o < 5 * CG; o += blockDim.x) {
-        const int which = o / CG, cc = o % CG;
-        if (which == 4 && !cta_exclusive) continue;
-        double acc = 0.0;
-#pragma unroll
-        for (int w = 0; w < kLikWarps; ++w) acc += red[w * 5 * CG + o];
-        if (which < 4)
-            p.part[((size_t)blockIdx.x * 4 + which) * Cp + blockIdx.y * CG + cc] = acc;
-        else
-            p.slots[((size_t)2 * p.NG + blockIdx.x) * Cp + blockIdx.y * CG + cc] = acc;
-    }
-    BGH_TRACE(4);
-}
-
-// ---------------------------------------------------------------------------------------------
-// per-chain closing formulas (priors, transforms, Jacobians) — ref: gene_regression.py:78-81,
-// heritability.py:45-49; PyMC3 3.6 distributions/continuous.py + transforms.py
-// ---------------------------------------------------------------------------------------------
-struct ChainSums {
-    double A_ll, A_e, S1, S2;
-};
-// Sum-independent per-chain terms of the closing formulas: computed once per evaluation, in
-// parallel with the partial-sum reduction (finalize) or directly (finish kernel).
-//   gene model: {iW, iW2, mi, lp0}   lp0 = all logp terms that do not involve the four sums
-//   gw model  : {sg0 (sigmoid of x0 when the intercept is "fixed"), -, mi, lp0}
-struct ChainConst {
-    double iW, iW2, mi, lp0;
-};
-
-__device__ ChainConst chain_const(const FinParams& p, int ch)
-{
-    const int Cp = p.Cp;
-    ChainConst c;
-    if (p.model == BGH_MODEL_GENE_NORMAL) {
-        const double xW = p.q[0 * Cp + ch], e = p.q[1 * Cp + ch], xm = p.q[2 * Cp + ch];
-        const double ax = fabs(xm);
-        const double u = exp(-ax);                 // one exp + one log1p serve sigmoid and both logs
-        const double L = log1p(u);
-        c.iW = exp(-xW);
-        c.iW2 = c.iW * c.iW;
-        c.mi = (xm >= 0.0 ? 1.0 : u) / (1.0 + u);
-        const double G = (double)p.G_total;
-        // log sigmoid(x) + log(1 - sigmoid(x)) = -|x| - 2 log1p(exp(-|x|))
-        double lp = (-c.iW - 2.0 * xW) + xW;                       // InverseGamma(1,1) + log-Jacobian
-        lp += -0.5 * (e - 1.0) * (e - 1.0) - 0.5 * kLog2Pi;        // Normal(1,1)
-        lp += -ax - 2.0 * L;                                       // Beta(1,1)=0 ; logodds Jacobian
-        lp += -G * xW - 0.5 * G * kLog2Pi;                         // Normal(beta | mi, W) constants
-        lp += p.lik_const;
-        c.lp0 = lp;
-    } else {
-        const double x0 = p.q[0 * Cp + ch], xm = p.q[1 * Cp + ch];
-        const double ax = fabs(xm);
-        const double u = exp(-ax);
-        const double L = log1p(u);
-        c.mi = (xm >= 0.0 ? 1.0 : u) / (1.0 + u);
-        const double l1m = (xm >= 0.0 ? -xm : 0.0) - L;            // log(1 - mi)
-        double lp = l1m + 0.69314718055994530942;                  // Beta(1,2)
-        lp += -ax - 2.0 * L;                                       // logodds Jacobian
-        c.iW = 0.0;
-        if (p.fix) {
-            // Uniform(lo,hi) logp = -log(hi-lo); interval Jacobian = log(hi-lo) + log sigmoid'(x0)
-            const double a0 = fabs(x0), u0 = exp(-a0);
-            c.iW = (x0 >= 0.0 ? 1.0 : u0) / (1.0 + u0);            // sigmoid(x0)
-            lp += -a0 - 2.0 * log1p(u0);
-        } else {
-            lp += -0.5 * (x0 - 1.0) * (x0 - 1.0) - 0.5 * kLog2Pi;
-        }
-        lp += p.lik_const;
-        c.iW2 = 0.0;
-        c.lp0 = lp;
-    }
-    return c;
-}
-
-__device__ __forceinline__ void finish_chain(const FinParams& p, int ch, const ChainSums& s, const ChainConst& c)
-{
-    const int Cp = p.Cp;
-    if (p.model == BGH_MODEL_GENE_NORMAL) {
-        const double e = p.q[1 * Cp + ch];
-        const double G = (double)p.G_total;
-        p.logp[ch] = c.lp0 - 0.5 * s.S2 * c.iW2 - 0.5 * s.A_ll;
-        p.grad[0 * Cp + ch] = c.iW - 1.0 + s.S2 * c.iW2 - G;
-        p.grad[1 * Cp + ch] = -(e - 1.0) + (p.fix ? 0.0 : s.A_e);
-        p.grad[2 * Cp + ch] = 1.0 - 2.0 * c.mi + c.mi * (1.0 - c.mi) * s.S1 * c.iW2;
-    } else {
-        const double x0 = p.q[0 * Cp + ch];
-        p.logp[ch] = c.lp0 - 0.5 * s.A_ll;
-        if (p.fix) {
-            const double sg = c.iW;
-            p.grad[0 * Cp + ch] = s.A_e * (kGwFixHi - kGwFixLo) * sg * (1.0 - sg) + (1.0 - 2.0 * sg);
-        } else {
-            p.grad[0 * Cp + ch] = -(x0 - 1.0) + s.A_e;
-        }
-    }
-}
-
-// gradient row of a gene from its total residual sum.  The per-chain constants (1/W^2, mi) were
-// computed by the likelihood kernel and left in p.cc, so no exp() chain sits on this path.
-struct GeneCoef {
-    double iW2, mi, beta;
-};
-__device__ __forceinline__ GeneCoef load_gene_coef(const FinParams& p, int gene, int ch, bool needed)
-{
-    GeneCoef gc;
-    gc.iW2 = gc.mi = gc.beta = 0.0;
-    if (needed) {
-        gc.iW2 = p.cc[0 * p.Cp + ch];
-        gc.mi = p.cc[1 * p.Cp + ch];
-        if (p.model == BGH_MODEL_GENE_NORMAL) gc.beta = p.q[(size_t)(3 + gene) * p.Cp + ch];
-    }
-    return gc;
-}
-__device__ __forceinline__ void finish_gene(const FinParams& p, int gene, int ch, double sum_r, const GeneCoef& gc)
-{
-    const int Cp = p.Cp;
-    if (p.model == BGH_MODEL_GENE_NORMAL) {
-        p.grad[(size_t)(3 + gene) * Cp + ch] = fma(p.c, sum_r, -(gc.beta - gc.mi) * gc.iW2);
-    } else {
-        // (c*sum_r - 1/(1-mi)) * mi(1-mi) + (1 - 2mi)
-        p.grad[1 * Cp + ch] = p.c * sum_r * gc.mi * (1.0 - gc.mi) + 1.0 - 3.0 * gc.mi;
-    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -26,60 +26,9 @@
 
 #include "bgh_internal.h"
 #include "bgh_sampler.h"
+#include "bgh_sampler_device.cuh"
 
 namespace bgh {
-
-// ---------------------------------------------------------------------------------------------
-// Philox4x32-10
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
-{
-    const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const unsigned hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
-        const unsigned hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += W0;
-        k.y += W1;
-    }
-    return c;
-}
-__device__ __forceinline__ double u01_open(unsigned a, unsigned b)
-{
-    // 53-bit uniform in (0, 1)
-    const unsigned long long x = ((unsigned long long)a << 21) ^ (unsigned long long)(b >> 11);
-    return ((double)(x & ((1ull << 53) - 1)) + 0.5) * (1.0 / 9007199254740992.0);
-}
-__device__ __forceinline__ uint2 chain_key(const NutsParams& p, int chain)
-{
-    return make_uint2((unsigned)(p.seed & 0xffffffffull) ^ (0x9E3779B9u * (unsigned)(chain + 1)),
-                      (unsigned)(p.seed >> 32) + (unsigned)chain);
-}
-enum : unsigned { kPurposeMomentum = 1, kPurposeDir = 2, kPurposeLeaf = 3, kPurposeTop = 4 };
-
-__device__ __forceinline__ double chain_uniform(const NutsParams& p, int chain, unsigned purpose, unsigned idx)
-{
-    const uint4 r = philox4x32_10(make_uint4((unsigned)p.draw, purpose, idx, (unsigned)(p.draw >> 32)), chain_key(p, chain));
-    return u01_open(r.x, r.y);
-}
-
-__device__ __forceinline__ double logaddexp_d(double a, double b)
-{
-    if (a == -INFINITY) return b;
-    if (b == -INFINITY) return a;
-    const double m = fmax(a, b);
-    return m + log1p(exp(-fabs(a - b)));
-}
-
-// vector slot accessor: state is [n_slots][D][Cp]
-__device__ __forceinline__ double* slot(const NutsParams& p, int s) { return p.state + (size_t)s * p.D * p.Cp; }
-__device__ __forceinline__ double* ckpt(const NutsParams& p, int which, int level)
-{
-    return p.ckpt + ((size_t)which * kNutsMaxDepth + level) * p.D * p.Cp;
-}
-__device__ __forceinline__ double& sc(const NutsParams& p, int k, int c) { return p.sc[(size_t)k * p.Cp + c]; }
-__device__ __forceinline__ int& fl(const NutsParams& p, int k, int c) { return p.fl[(size_t)k * p.Cp + c]; }
 
 // Work distribution of the vector kernels: a CTA owns kRowsPerCta-row strips; thread -> (row-in-strip, chain).
 // Per-chain partial sums are reduced inside the CTA in a fixed order and written to
@@ -298,13 +247,13 @@ __global__ void __launch_bounds__(kVecThreads) nuts_leap2_kernel(const NutsParam
             const double ps = (leaf == 0) ? mom : PSR[i] + mom;
             PSR[i] = ps;
             if (store_level >= 0) {
-                ckpt(p, 0, store_level)[i] = mom;
-                ckpt(p, 1, store_level)[i] = ps;
+                *ckpt2(p, store_level, i) = make_double2(mom, ps);
             }
 #pragma unroll
             for (int l = 0; l < NL; ++l) {
-                const double pc = ckpt(p, 0, lvl_min + l)[i];
-                const double sub = ps - ckpt(p, 1, lvl_min + l)[i] + pc;   // p_sum of the aligned block
+                const double2 ck = *ckpt2(p, lvl_min + l, i);
+                const double pc = ck.x;
+                const double sub = ps - ck.y + pc;   // p_sum of the aligned block
                 acc[1 + 2 * l] = fma(sub, var * pc, acc[1 + 2 * l]);       // . v_left
                 acc[2 + 2 * l] = fma(sub, vel, acc[2 + 2 * l]);            // . v_right
             }
@@ -649,278 +598,6 @@ __device__ __forceinline__ double chain_uniform_at(const NutsParams& p, int chai
     return u01_open(r.x, r.y);
 }
 
-// ---- tick, vector part 1: pending end-of-doubling ops, trace record, mass-matrix adaptation, momentum
-// refresh of chains that start a transition, then the first half of the leapfrog for every running chain
-__global__ void __launch_bounds__(kVecThreads) nuts_async_pre_kernel(const AsyncParams a)
-{
-    const NutsParams& p = a.n;
-    const VecIdx v = vec_index(p);
-    double acc[1] = {0.0};
-    const int c = v.chain;
-    const int phase = v.on ? afl(a, kAfPhase, c) : kPhaseFinished;
-    if (phase != kPhaseFinished) {
-        const bool merge = afl(a, kAfMerge, c) != 0, take = afl(a, kAfTake, c) != 0, take_top = afl(a, kAfTakeTop, c) != 0;
-        const bool is_new = afl(a, kAfNew, c) != 0, is_first = afl(a, kAfFirst, c) != 0;
-        const bool adapt = afl(a, kAfAdapt, c) != 0, sw = afl(a, kAfSwitch, c) != 0;
-        const int rec_slot = afl(a, kAfRecSlot, c);
-        const int dir = afl(a, kAfDir, c), dir_prev = afl(a, kAfDirPrev, c);
-        const long long draw = afl(a, kAfDraw, c);
-        const double h = sc(p, kScH, c);
-        const double fg_w = sc(p, kScFgUse, c), bg_w = sc(p, kScBgUse, c);
-        const uint2 key = chain_key(p, c);
-        double* const VAR = slot(p, kSlotVar);
-        double* const QW = slot(p, kSlotQW);
-        double* const PW = slot(p, kSlotPW);
-        double* const GW = slot(p, kSlotGW);
-        double* const QS = slot(p, kSlotQS);
-        double* const GS = slot(p, kSlotGS);
-        double* const QP = slot(p, kSlotQP);
-        double* const GP = slot(p, kSlotGP);
-        double* const PST = slot(p, kSlotPSumTree);
-        const double* const PSR = slot(p, kSlotPSumRun);
-        double* const QL = slot(p, kSlotQL);
-        double* const PL = slot(p, kSlotPL);
-        double* const GL = slot(p, kSlotGL);
-        double* const QR = slot(p, kSlotQR);
-        double* const PR = slot(p, kSlotPR);
-        double* const GR = slot(p, kSlotGR);
-        double* const FM = slot(p, kSlotFgMean);
-        double* const FR = slot(p, kSlotFgRaw);
-        double* const BM = slot(p, kSlotBgMean);
-        double* const BR = slot(p, kSlotBgRaw);
-        for (int d = v.r0; d < p.D; d += v.rstep) {
-            const size_t i = (size_t)d * p.Cp + c;
-            double qw = QW[i], pw = PW[i], gw = GW[i];
-            bool edge_in_regs = false;
-            double qp = 0.0, gp = 0.0;
-            bool have_prop = false;
-            if (merge) {     // the doubling that ended last tick was valid: fold it into the tree
-                double qs = qw, gs = gw;
-                if (take) { QS[i] = qw; GS[i] = gw; }
-                if (take_top) {
-                    if (!take) { qs = QS[i]; gs = GS[i]; }
-                    QP[i] = qs; GP[i] = gs;
-                    qp = qs; gp = gs; have_prop = true;
-                }
-                if (dir_prev > 0) { QR[i] = qw; PR[i] = pw; GR[i] = gw; }
-                else { QL[i] = qw; PL[i] = pw; GL[i] = gw; }
-                PST[i] = PST[i] + PSR[i];
-                edge_in_regs = true;
-            }
-            if (is_new || phase == kPhaseFlush) {
-                if (!have_prop) { qp = QP[i]; gp = GP[i]; }
-                if (rec_slot >= 0 && c < p.C) {
-                    const size_t t = ((size_t)rec_slot * p.D + d) * p.C + c;
-                    if (a.trace_f32) reinterpret_cast<float*>(a.trace)[t] = (float)qp;
-                    else reinterpret_cast<double*>(a.trace)[t] = qp;
-                }
-            }
-            if (phase == kPhaseFlush) continue;
-            double q, mom, g, var = VAR[i];
-            if (is_new) {
-                if (adapt) {   // quadpotential.QuadPotentialDiagAdapt.update with the sample just produced
-                    double fm = FM[i], fr = FR[i], bm = BM[i], br = BR[i];
-                    { const double od = qp - fm; fm += od / fg_w; fr = fma(od, qp - fm, fr); }
-                    { const double od = qp - bm; bm += od / bg_w; br = fma(od, qp - bm, br); }
-                    var = fr / fg_w;
-                    VAR[i] = var;
-                    if (sw) { FM[i] = bm; FR[i] = br; BM[i] = 0.0; BR[i] = 0.0; }
-                    else { FM[i] = fm; FR[i] = fr; BM[i] = bm; BR[i] = br; }
-                }
-                const unsigned gd = (unsigned)(p.coord_offset + d);
-                const uint4 r = philox4x32_10(make_uint4((unsigned)draw, kPurposeMomentum, gd, (unsigned)(draw >> 32)), key);
-                const double u1 = u01_open(r.x, r.y), u2 = u01_open(r.z, r.w);
-                const double z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
-                mom = z * rsqrt(var);
-                PL[i] = mom; PR[i] = mom; PST[i] = mom;
-                QL[i] = qp; QR[i] = qp; GL[i] = gp; GR[i] = gp;
-                acc[0] = fma(0.5 * var * mom, mom, acc[0]);
-                q = qp; g = gp;
-            } else if (is_first) {
-                if (edge_in_regs && dir == dir_prev) { q = qw; mom = pw; g = gw; }
-                else if (dir > 0) { q = QR[i]; mom = PR[i]; g = GR[i]; }
-                else { q = QL[i]; mom = PL[i]; g = GL[i]; }
-            } else {
-                q = qw; mom = pw; g = gw;
-                if (take) { QS[i] = q; GS[i] = g; }
-            }
-            const double ph = fma(h, g, mom);
-            PW[i] = ph;
-            QW[i] = fma(2.0 * h * var, ph, q);
-        }
-    }
-    // kinetic energy of the fresh momenta -> quantity kAqKin0
-    {
-        __shared__ double red[kVecThreads];
-        const int tpr = p.Cp < kVecThreads ? p.Cp : kVecThreads;
-        const int rpb = kVecThreads / tpr;
-        red[threadIdx.x] = acc[0];
-        __syncthreads();
-        if (threadIdx.x < tpr && v.on) {
-            double t = 0.0;
-            for (int r = 0; r < rpb; ++r) t += red[r * tpr + threadIdx.x];
-            p.partials[((size_t)blockIdx.x * kAsyncPartials + kAqKin0) * p.Cp + c] = t;
-        }
-    }
-}
-
-// ---- tick, vector part 2: second half kick + per-chain reductions (kinetic, sub-block U-turn dots for
-// the chain's own checkpoint levels, speculative whole-tree dots on the last leaf of a doubling)
-__global__ void __launch_bounds__(kVecThreads) nuts_async_post_kernel(const AsyncParams a)
-{
-    const NutsParams& p = a.n;
-    const VecIdx v = vec_index(p);
-    constexpr int NQ = kAqTree0 + 2;
-    double acc[NQ];
-#pragma unroll
-    for (int k = 0; k < NQ; ++k) acc[k] = 0.0;
-    const int c = v.chain;
-    const bool on = v.on && afl(a, kAfPhase, c) == kPhaseRun;
-    int n_lvl = 0;
-    if (on) {
-        const int dir = afl(a, kAfDir, c), leaf = afl(a, kAfLeaf, c), store_level = afl(a, kAfStoreLevel, c);
-        const int lvl_min = afl(a, kAfLvlMin, c);
-        n_lvl = afl(a, kAfNLvl, c);
-        const bool last = afl(a, kAfLastLeaf, c) != 0;
-        const double h = sc(p, kScH, c);
-        const double* const VAR = slot(p, kSlotVar);
-        double* const PW = slot(p, kSlotPW);
-        const double* const GW = slot(p, kSlotGW);
-        double* const PSR = slot(p, kSlotPSumRun);
-        const double* const PST = slot(p, kSlotPSumTree);
-        const double* const PO = slot(p, dir > 0 ? kSlotPL : kSlotPR);
-        for (int d = v.r0; d < p.D; d += v.rstep) {
-            const size_t i = (size_t)d * p.Cp + c;
-            const double var = VAR[i];
-            const double mom = fma(h, GW[i], PW[i]);
-            PW[i] = mom;
-            const double vel = var * mom;
-            acc[0] = fma(0.5 * vel, mom, acc[0]);
-            const double ps = (leaf == 0) ? mom : PSR[i] + mom;
-            PSR[i] = ps;
-            if (store_level >= 0) {
-                ckpt(p, 0, store_level)[i] = mom;
-                ckpt(p, 1, store_level)[i] = ps;
-            }
-#pragma unroll
-            for (int l = 0; l < kNutsMaxDepth; ++l) {
-                if (l < n_lvl) {
-                    const double pc = ckpt(p, 0, lvl_min + l)[i];
-                    const double sub = ps - ckpt(p, 1, lvl_min + l)[i] + pc;
-                    acc[1 + 2 * l] = fma(sub, var * pc, acc[1 + 2 * l]);
-                    acc[2 + 2 * l] = fma(sub, vel, acc[2 + 2 * l]);
-                }
-            }
-            if (last) {
-                const double pst = PST[i] + ps;
-                acc[kAqTree0] = fma(pst, vel, acc[kAqTree0]);
-                acc[kAqTree0 + 1] = fma(pst, var * PO[i], acc[kAqTree0 + 1]);
-            }
-        }
-    }
-    // CTA reduction in a fixed order; quantities beyond the deepest level in use by this CTA are zero
-    __shared__ double red[kVecThreads];
-    __shared__ int nl_max;
-    if (threadIdx.x == 0) nl_max = 0;
-    __syncthreads();
-    if (n_lvl > 0) atomicMax(&nl_max, n_lvl);
-    __syncthreads();
-    const int nl = nl_max;
-    const int tpr = p.Cp < kVecThreads ? p.Cp : kVecThreads;
-    const int rpb = kVecThreads / tpr;
-#pragma unroll
-    for (int k = 0; k < NQ; ++k) {
-        const bool used = (k == 0) || (k <= 2 * nl) || (k >= kAqTree0);   // CTA-uniform
-        if (!used) continue;                                            // never read by the sparse reduction
-        red[threadIdx.x] = acc[k];
-        __syncthreads();
-        if (threadIdx.x < tpr && v.on) {
-            double t = 0.0;
-            for (int r = 0; r < rpb; ++r) t += red[r * tpr + threadIdx.x];
-            p.partials[((size_t)blockIdx.x * kAsyncPartials + k) * p.Cp + c] = t;
-        }
-        __syncthreads();
-    }
-}
-
-// Single-CTA SPARSE reduction of the async partials into p.sums[kAsyncPartials][Cp]: a chain only
-// needs the quantities of its own tick (kinetic; 2 dots per checkpoint level it checks; the two
-// whole-tree dots on the last leaf of a doubling; kinetic0 when it started a transition), typically
-// 3-4 of the 24.  The needed (quantity, chain) pairs are listed in shared memory, then R row groups
-// sum independent strips of the block partials and one thread per pair adds the R strip sums in a
-// fixed order (deterministic).
-constexpr int kMaxNeeded = 4096;
-__device__ void reduce_async_partials(const AsyncParams& a)
-{
-    const NutsParams& p = a.n;
-    __shared__ double stage[kScThreads];
-    __shared__ unsigned short need_k[kMaxNeeded], need_c[kMaxNeeded];
-    __shared__ int n_need;
-    __shared__ int warp_tot[kScThreads / 32];
-    const int tid = threadIdx.x;
-    // every thread owns one chain (Cp <= kScThreads): count its needed quantities, block-scan the
-    // counts, then write its own list entries
-    int cnt = 0, nl = 0, last = 0, isnew = 0;
-    if (tid < p.Cp && afl(a, kAfPhase, tid) == kPhaseRun) {
-        nl = afl(a, kAfNLvl, tid);
-        last = afl(a, kAfLastLeaf, tid) ? 1 : 0;
-        isnew = afl(a, kAfNew, tid) ? 1 : 0;
-        cnt = 1 + 2 * nl + 2 * last + isnew;
-    }
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((tid & 31) >= o) incl += t;
-    }
-    if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
-    __syncthreads();
-    if (tid < 32) {
-        int w = warp_tot[tid];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, w, o);
-            if (tid >= o) w += t;
-        }
-        warp_tot[tid] = w;
-        if (tid == 31) n_need = w;
-    }
-    __syncthreads();
-    {
-        int n = incl - cnt + ((tid >> 5) > 0 ? warp_tot[(tid >> 5) - 1] : 0);
-        if (cnt > 0 && n + cnt <= kMaxNeeded) {
-            need_k[n] = 0; need_c[n] = (unsigned short)tid; ++n;
-            for (int l = 0; l < 2 * nl; ++l) { need_k[n] = (unsigned short)(1 + l); need_c[n] = (unsigned short)tid; ++n; }
-            if (last) {
-                need_k[n] = kAqTree0; need_c[n] = (unsigned short)tid; ++n;
-                need_k[n] = kAqTree0 + 1; need_c[n] = (unsigned short)tid; ++n;
-            }
-            if (isnew) { need_k[n] = kAqKin0; need_c[n] = (unsigned short)tid; ++n; }
-        }
-    }
-    __syncthreads();
-    const int n_out = min(n_need, kMaxNeeded);
-    for (int o0 = 0; o0 < n_out; o0 += kScThreads) {
-        const int nb = min(kScThreads, n_out - o0);
-        const int R = kScThreads / nb;
-        const int oo = tid % nb, sub = tid / nb;
-        const int k = need_k[o0 + oo], c = need_c[o0 + oo];
-        double acc = 0.0;
-        if (sub < R) {
-#pragma unroll 8
-            for (int b = sub; b < p.n_vec_blocks; b += R) acc += p.partials[((size_t)b * kAsyncPartials + k) * p.Cp + c];
-        }
-        stage[tid] = acc;
-        __syncthreads();
-        if (tid < nb) {
-            double t = 0.0;
-            for (int r = 0; r < R; ++r) t += stage[r * nb + tid];
-            p.sums[(size_t)k * p.Cp + c] = t;
-        }
-        __syncthreads();
-    }
-}
-
 __device__ __forceinline__ void schedule_leaf(const AsyncParams& a, int c, int leaf, int depth)
 {
     // checkpoint bookkeeping of the iterative tree for leaf index `leaf` of a doubling of depth `depth`
@@ -941,182 +618,8 @@ __device__ __forceinline__ void schedule_leaf(const AsyncParams& a, int c, int l
     afl(a, kAfLastLeaf, c) = (leaf == (1 << depth) - 1) ? 1 : 0;
 }
 
-// ---- tick, scalar part: the per-chain NUTS state machine
-__global__ void __launch_bounds__(kScThreads) nuts_async_scalar_kernel(const AsyncParams a)
-{
-    const NutsParams& p = a.n;
-    __shared__ int n_fin;
-    if (threadIdx.x == 0) n_fin = 0;
-    reduce_async_partials(a);
-    for (int c = threadIdx.x; c < p.Cp; c += blockDim.x) {
-        int phase = afl(a, kAfPhase, c);
-        if (phase == kPhaseFlush) {
-            phase = kPhaseFinished;
-            afl(a, kAfPhase, c) = phase;
-            afl(a, kAfMerge, c) = 0; afl(a, kAfTake, c) = 0; afl(a, kAfTakeTop, c) = 0; afl(a, kAfRecSlot, c) = -1;
-        }
-        if (phase == kPhaseFinished) {
-            if (c < p.C) atomicAdd(&n_fin, 1);
-            continue;
-        }
-        long long draw = afl(a, kAfDraw, c);
-        int depth = afl(a, kAfDepth, c), leaf = afl(a, kAfLeaf, c), dir = afl(a, kAfDir, c);
-        if (afl(a, kAfNew, c)) {      // the transition began this tick
-            const double e0 = sum_partials(p, kAqKin0, c) - sc(p, kScLogpProp, c);
-            sc(p, kScE0, c) = e0;
-            sc(p, kScEnergyProp, c) = e0;
-            sc(p, kScLogSizeTree, c) = 0.0;
-            sc(p, kScAcceptSum, c) = 0.0;
-            sc(p, kScNProp, c) = 0.0;
-            sc(p, kScMaxDE, c) = 0.0;
-            afl(a, kAfDiverging, c) = 0;
-            afl(a, kAfTurning, c) = 0;
-            if (!isfinite(e0)) afl(a, kAfBadStart, c) = 1;
-        }
-        afl(a, kAfNew, c) = 0; afl(a, kAfFirst, c) = 0; afl(a, kAfMerge, c) = 0; afl(a, kAfTakeTop, c) = 0;
-        afl(a, kAfTake, c) = 0; afl(a, kAfAdapt, c) = 0; afl(a, kAfSwitch, c) = 0; afl(a, kAfRecSlot, c) = -1;
-
-        // ---- the leaf just integrated (same logic as nuts_leaf_scalar_kernel)
-        const double kin = sum_partials(p, 0, c);
-        const double logp = p.logp_w[c];
-        const double energy = kin - logp;
-        double dE = energy - sc(p, kScE0, c);
-        if (isnan(dE)) dE = INFINITY;
-        if (fabs(dE) > fabs(sc(p, kScMaxDE, c))) sc(p, kScMaxDE, c) = dE;
-        sc(p, kScNProp, c) += 1.0;
-        bool valid = true;
-        if (fabs(dE) < p.emax) {
-            sc(p, kScAcceptSum, c) += fmin(1.0, exp(-dE));
-            const double lw = -dE;
-            bool take;
-            if (leaf == 0) {
-                take = true;
-                sc(p, kScLogSizeSub, c) = lw;
-            } else {
-                const double ls = logaddexp_d(sc(p, kScLogSizeSub, c), lw);
-                const double u = chain_uniform_at(p, c, draw, kPurposeLeaf, ((unsigned)depth << 16) | (unsigned)leaf);
-                take = log(u) < lw - ls;
-                sc(p, kScLogSizeSub, c) = ls;
-            }
-            if (take) {
-                afl(a, kAfTake, c) = 1;
-                sc(p, kScLogpSub, c) = logp;
-                sc(p, kScEnergySub, c) = energy;
-            }
-            const int n_lvl = afl(a, kAfNLvl, c);
-            bool turning = false;
-            for (int l = 0; l < n_lvl; ++l)
-                turning = turning || (sum_partials(p, 1 + 2 * l, c) <= 0.0) || (sum_partials(p, 2 + 2 * l, c) <= 0.0);
-            if (turning) {
-                afl(a, kAfTurning, c) = 1;
-                valid = false;
-            }
-        } else {
-            afl(a, kAfDiverging, c) = 1;
-            valid = false;
-        }
-
-        const int max_depth = (draw < a.tune && draw < a.early_draws) ? a.early_depth : a.max_depth;
-        bool end_transition = false;
-        if (!valid) {
-            end_transition = true;
-            afl(a, kAfTake, c) = 0;
-            depth += 1;                                       // PyMC3 counts the discarded doubling in `depth`
-        } else if (leaf == (1 << depth) - 1) {
-            const double s1 = sc(p, kScLogSizeTree, c), s2 = sc(p, kScLogSizeSub, c);
-            const double u = chain_uniform_at(p, c, draw, kPurposeTop, (unsigned)depth);
-            if (log(u) < s2 - s1) {
-                afl(a, kAfTakeTop, c) = 1;
-                sc(p, kScLogpProp, c) = sc(p, kScLogpSub, c);
-                sc(p, kScEnergyProp, c) = sc(p, kScEnergySub, c);
-            }
-            sc(p, kScLogSizeTree, c) = logaddexp_d(s1, s2);
-            afl(a, kAfMerge, c) = 1;
-            afl(a, kAfDirPrev, c) = dir;
-            depth += 1;
-            if (sum_partials(p, kAqTree0, c) <= 0.0 || sum_partials(p, kAqTree0 + 1, c) <= 0.0) {
-                afl(a, kAfTurning, c) = 1;
-                end_transition = true;
-            }
-            if (depth >= max_depth) end_transition = true;
-            if (!end_transition) {
-                const double ud = chain_uniform_at(p, c, draw, kPurposeDir, (unsigned)depth);
-                dir = (ud < 0.5) ? 1 : -1;
-                leaf = 0;
-                afl(a, kAfFirst, c) = 1;
-                sc(p, kScLogSizeSub, c) = -INFINITY;
-            }
-        } else {
-            leaf += 1;
-        }
-
-        if (end_transition) {
-            const bool tuning = draw < a.tune;
-            const double n = fmax(sc(p, kScNProp, c), 1.0);
-            const double accept = sc(p, kScAcceptSum, c) / n;
-            const double eps_used = sc(p, kScEps, c);
-            if (tuning) {     // step_size.DualAverageAdaptation.update
-                const double count = sc(p, kScDaCount, c);
-                const double w = 1.0 / (count + p.da_t0);
-                const double hbar = (1.0 - w) * sc(p, kScDaHbar, c) + w * (p.target_accept - accept);
-                const double log_step = sc(p, kScDaMu, c) - hbar * sqrt(count) / p.da_gamma;
-                const double mk = pow(count, -p.da_kappa);
-                sc(p, kScDaLogBar, c) = mk * log_step + (1.0 - mk) * sc(p, kScDaLogBar, c);
-                sc(p, kScDaHbar, c) = hbar;
-                sc(p, kScDaCount, c) = count + 1.0;
-                sc(p, kScDaLogStep, c) = log_step;
-                sc(p, kScEps, c) = exp(log_step);
-            }
-            if (a.stats && c < p.C) {
-                double* st = a.stats + (size_t)draw * BGH_NUTS_N_STATS * p.C;
-                st[0 * p.C + c] = (double)depth;
-                st[1 * p.C + c] = accept;
-                st[2 * p.C + c] = sc(p, kScNProp, c);
-                st[3 * p.C + c] = (double)afl(a, kAfDiverging, c);
-                st[4 * p.C + c] = sc(p, kScEnergyProp, c);
-                st[5 * p.C + c] = tuning ? sc(p, kScEps, c) : eps_used;
-                st[6 * p.C + c] = sc(p, kScLogpProp, c);
-                st[7 * p.C + c] = sc(p, kScMaxDE, c);
-            }
-            afl(a, kAfRecSlot, c) = (draw >= a.tune) ? (int)(draw - a.tune) : -1;
-            if (tuning) {     // QuadPotentialDiagAdapt.update schedule
-                const int n_adapt = afl(a, kAfNAdapt, c);
-                double fg = sc(p, kScFgW, c) + 1.0, bg = sc(p, kScBgW, c) + 1.0;
-                sc(p, kScFgUse, c) = fg;
-                sc(p, kScBgUse, c) = bg;
-                afl(a, kAfAdapt, c) = 1;
-                const int sw = (n_adapt > 0 && n_adapt % a.window == 0) ? 1 : 0;
-                afl(a, kAfSwitch, c) = sw;
-                if (sw) { fg = bg; bg = 0.0; }
-                sc(p, kScFgW, c) = fg;
-                sc(p, kScBgW, c) = bg;
-                afl(a, kAfNAdapt, c) = n_adapt + 1;
-            }
-            draw += 1;
-            if (draw == a.tune) sc(p, kScEps, c) = exp(sc(p, kScDaLogBar, c));    // stop tuning
-            if (draw >= (long long)a.tune + a.draws) {
-                phase = kPhaseFlush;
-            } else {
-                afl(a, kAfNew, c) = 1;
-                depth = 0;
-                leaf = 0;
-                const double ud = chain_uniform_at(p, c, draw, kPurposeDir, 0u);
-                dir = (ud < 0.5) ? 1 : -1;
-                sc(p, kScLogSizeSub, c) = -INFINITY;
-            }
-        }
-        afl(a, kAfPhase, c) = phase;
-        afl(a, kAfDraw, c) = (int)draw;
-        afl(a, kAfDepth, c) = depth;
-        afl(a, kAfLeaf, c) = leaf;
-        afl(a, kAfDir, c) = dir;
-        sc(p, kScH, c) = 0.5 * sc(p, kScEps, c) * (double)dir;
-        schedule_leaf(a, c, leaf, depth);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) *a.n_finished = n_fin;
-}
-
+// The tick itself (pre / likelihood / finalize / post / scalar) is the persistent kernel in bgh_fused.cu;
+// only the initialisation of the per-chain machine state lives here.
 __global__ void nuts_async_init_kernel(const AsyncParams a, double step0, double initial_weight)
 {
     const NutsParams& p = a.n;
@@ -1147,17 +650,6 @@ __global__ void nuts_async_init_kernel(const AsyncParams a, double step0, double
     if (c == 0) *a.n_finished = 0;
 }
 
-cudaError_t nuts_async_launch_pre(const AsyncParams& a, cudaStream_t s)
-{
-    nuts_async_pre_kernel<<<vec_grid(a.n), kVecThreads, 0, s>>>(a);
-    return cudaGetLastError();
-}
-cudaError_t nuts_async_launch_post(const AsyncParams& a, cudaStream_t s)
-{
-    nuts_async_post_kernel<<<vec_grid(a.n), kVecThreads, 0, s>>>(a);
-    nuts_async_scalar_kernel<<<1, kScThreads, 0, s>>>(a);
-    return cudaGetLastError();
-}
 cudaError_t nuts_async_launch_init(const AsyncParams& a, double step0, double initial_weight, cudaStream_t s)
 {
     nuts_async_init_kernel<<<(a.n.Cp + 127) / 128, 128, 0, s>>>(a, step0, initial_weight);

@@ -96,8 +96,6 @@ struct AsyncParams {
     int tune, draws;
     int early_draws, early_depth, max_depth, window;
 };
-cudaError_t nuts_async_launch_pre(const AsyncParams& p, cudaStream_t s);
-cudaError_t nuts_async_launch_post(const AsyncParams& p, cudaStream_t s);
 cudaError_t nuts_async_launch_init(const AsyncParams& p, double step0, double initial_weight, cudaStream_t s);   // leap1, leap2, leaf scalar (plus the likelihood + finalize)
 
 }  // namespace bgh
