@@ -71,7 +71,7 @@ class bgh_nuts_async_buffers(ctypes.Structure):
 
 
 NUTS_ASYNC_N_FL, NUTS_ASYNC_N_SC, NUTS_ASYNC_PARTIALS = 24, 24, 24
-NUTS_MAX_DEPTH, NUTS_N_SLOTS, NUTS_N_SC, NUTS_N_FL, NUTS_N_STATS = 10, 20, 16, 11, 8
+NUTS_MAX_DEPTH, NUTS_N_SLOTS, NUTS_N_SC, NUTS_N_FL, NUTS_N_STATS = 10, 21, 16, 11, 8
 NUTS_MAX_PARTIALS = 1 + 2 * NUTS_MAX_DEPTH
 NUTS_SLOT_Q, NUTS_SLOT_GRAD, NUTS_SLOT_VAR = 0, 1, 2
 NUTS_SLOT_FG_MEAN, NUTS_SLOT_FG_RAW, NUTS_SLOT_BG_MEAN, NUTS_SLOT_BG_RAW = 16, 17, 18, 19

@@ -979,7 +979,7 @@ int bgh_nuts_run(bgh_ctx* ctx, const bgh_nuts_async_buffers* buf, const bgh_nuts
     if (rc != BGH_OK) return rc;
     if (!buf->afl || (draws > 0 && !buf->trace) || tune < 0 || draws < 0 || tune + draws <= 0)
         return fail(ctx, BGH_EINVAL, "bgh_nuts_run: bad argument");
-    if (ctx->Cp > kLikThreads) return fail(ctx, BGH_EINVAL, "bgh_nuts_run: at most 512 chains per context (use several contexts / GPUs)");
+    if (ctx->Cp > 128) return fail(ctx, BGH_EINVAL, "bgh_nuts_run: at most 128 chains per context (use several contexts / GPUs)");
     if (poll_ticks <= 0) poll_ticks = 64;
     a.afl = buf->afl; a.trace = buf->trace; a.stats = buf->run_stats; a.n_finished = buf->base.n_active_dev;
     a.trace_f32 = buf->trace_f32; a.tune = tune; a.draws = draws;

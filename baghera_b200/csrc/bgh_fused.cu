@@ -27,6 +27,12 @@
 #ifndef BGH_POST_HOIST
 #define BGH_POST_HOIST 6
 #endif
+#ifndef BGH_POST_J
+#define BGH_POST_J 2
+#endif
+#ifndef BGH_POST_HL
+#define BGH_POST_HL 2
+#endif
 
 namespace bgh {
 
@@ -233,6 +239,16 @@ __device__ __forceinline__ double chain_uniform_at(const NutsParams& p, int chai
     return u01_open(r.x, r.y);
 }
 
+// tools only: globaltimer stamps of thread 0 of every CTA, 16 slots per (tick, CTA), first 8 traced ticks
+struct PhaseTrace {
+    unsigned long long* buf;   // NULL in production
+    int row;                   // (traced tick index * n_cta + cta) or -1
+};
+__device__ __forceinline__ void stamp(const PhaseTrace& pt, int k)
+{
+    if (pt.buf != nullptr && pt.row >= 0 && threadIdx.x == 0) pt.buf[(size_t)pt.row * 16 + k] = global_timer_ns();
+}
+
 struct TickIdx {
     int chain, r0, rstep, tpr, rpb;
     bool on;
@@ -250,8 +266,14 @@ __device__ __forceinline__ TickIdx tick_index(const NutsParams& p)
 }
 
 // ---- tick, vector part 1: pending end-of-doubling ops, trace record, mass-matrix adaptation, momentum
-// refresh of chains that start a transition, then the first half of the leapfrog for every running chain
-__device__ __forceinline__ void tick_pre(const AsyncParams& a, unsigned char* smem_raw)
+// refresh of chains that start a transition, then the first half of the leapfrog for every running chain.
+// Two rows per iteration, every load of both rows issued before the first store (the phase is bound by
+// memory latency x serial iterations, not by bytes).
+struct PreLoads {
+    double qw, pw, gw, var, qs, gs, pst, psr, qp, gp, fm, fr, bm, br, qe, pe, ge, z;
+};
+
+__device__ __forceinline__ void tick_pre(const AsyncParams& a, unsigned char* smem_raw, const PhaseTrace& pt)
 {
     const NutsParams& p = a.n;
     const TickIdx v = tick_index(p);
@@ -264,10 +286,9 @@ __device__ __forceinline__ void tick_pre(const AsyncParams& a, unsigned char* sm
         const bool adapt = afl(a, kAfAdapt, c) != 0, sw = afl(a, kAfSwitch, c) != 0;
         const int rec_slot = afl(a, kAfRecSlot, c);
         const int dir = afl(a, kAfDir, c), dir_prev = afl(a, kAfDirPrev, c);
-        const long long draw = afl(a, kAfDraw, c);
         const double h = sc(p, kScH, c);
-        const double fg_w = sc(p, kScFgUse, c), bg_w = sc(p, kScBgUse, c);
-        const uint2 key = chain_key(p, c);
+        double inv_fg = 0.0, inv_bg = 0.0;
+        if (is_new && adapt) { inv_fg = 1.0 / sc(p, kScFgUse, c); inv_bg = 1.0 / sc(p, kScBgUse, c); }
         double* const VAR = slot(p, kSlotVar);
         double* const QW = slot(p, kSlotQW);
         double* const PW = slot(p, kSlotPW);
@@ -288,70 +309,86 @@ __device__ __forceinline__ void tick_pre(const AsyncParams& a, unsigned char* sm
         double* const FR = slot(p, kSlotFgRaw);
         double* const BM = slot(p, kSlotBgMean);
         double* const BR = slot(p, kSlotBgRaw);
+        const double* const Z = slot(p, kSlotZ);
         // per-chain, loop-invariant load predicates
         const bool flush = phase == kPhaseFlush;
         const bool ld_s = merge && take_top && !take;                 // proposal of the finished subtree
         const bool ld_prop = (is_new || flush) && !(merge && take_top);
-        const bool edge_in_regs = merge;
-        const bool ld_edge = !flush && !is_new && is_first && !(edge_in_regs && dir == dir_prev);
+        const bool ld_adapt = is_new && adapt && !flush;
+        const bool ld_z = is_new && !flush;
+        const bool ld_edge = !flush && !is_new && is_first && !(merge && dir == dir_prev);
         const double* const QE = dir > 0 ? QR : QL;
         const double* const PE = dir > 0 ? PR : PL;
         const double* const GE = dir > 0 ? GR : GL;
-        for (int d = v.r0; d < p.D; d += v.rstep) {
+
+        auto load = [&](int d, PreLoads& L) {
             const size_t i = (size_t)d * p.Cp + c;
-            // ---- all loads of this element up front (independent -> one memory round trip)
-            const double qw = QW[i], pw = PW[i], gw = GW[i];
-            double var = VAR[i];
-            double qs = qw, gs = gw, pst = 0.0, psr = 0.0, qp = 0.0, gp = 0.0;
-            double fm = 0.0, fr = 0.0, bm = 0.0, br = 0.0, qe = 0.0, pe = 0.0, ge = 0.0;
-            if (ld_s) { qs = QS[i]; gs = GS[i]; }
-            if (merge) { pst = PST[i]; psr = PSR[i]; }
-            if (ld_prop) { qp = QP[i]; gp = GP[i]; }
-            if (is_new && adapt) { fm = FM[i]; fr = FR[i]; bm = BM[i]; br = BR[i]; }
-            if (ld_edge) { qe = QE[i]; pe = PE[i]; ge = GE[i]; }
+            L.qw = QW[i]; L.pw = PW[i]; L.gw = GW[i]; L.var = VAR[i];
+            L.qs = L.qw; L.gs = L.gw;
+            L.pst = L.psr = L.qp = L.gp = L.fm = L.fr = L.bm = L.br = L.qe = L.pe = L.ge = L.z = 0.0;
+            if (ld_s) { L.qs = QS[i]; L.gs = GS[i]; }
+            if (merge) { L.pst = PST[i]; L.psr = PSR[i]; }
+            if (ld_prop) { L.qp = QP[i]; L.gp = GP[i]; }
+            if (ld_adapt) { L.fm = FM[i]; L.fr = FR[i]; L.bm = BM[i]; L.br = BR[i]; }
+            if (ld_z) L.z = Z[i];
+            if (ld_edge) { L.qe = QE[i]; L.pe = PE[i]; L.ge = GE[i]; }
+        };
+        auto process = [&](int d, PreLoads& L) {
+            const size_t i = (size_t)d * p.Cp + c;
+            double qp = L.qp, gp = L.gp;
             // ---- the doubling that ended last tick was valid: fold it into the tree
             if (merge) {
-                if (take) { QS[i] = qw; GS[i] = gw; }
-                if (take_top) { QP[i] = qs; GP[i] = gs; qp = qs; gp = gs; }
-                if (dir_prev > 0) { QR[i] = qw; PR[i] = pw; GR[i] = gw; }
-                else { QL[i] = qw; PL[i] = pw; GL[i] = gw; }
-                PST[i] = pst + psr;
+                if (take) { QS[i] = L.qw; GS[i] = L.gw; }
+                if (take_top) { QP[i] = L.qs; GP[i] = L.gs; qp = L.qs; gp = L.gs; }
+                if (dir_prev > 0) { QR[i] = L.qw; PR[i] = L.pw; GR[i] = L.gw; }
+                else { QL[i] = L.qw; PL[i] = L.pw; GL[i] = L.gw; }
+                PST[i] = L.pst + L.psr;
             }
             if ((is_new || flush) && rec_slot >= 0 && c < p.C) {
                 const size_t t = ((size_t)rec_slot * p.D + d) * p.C + c;
                 if (a.trace_f32) reinterpret_cast<float*>(a.trace)[t] = (float)qp;
                 else reinterpret_cast<double*>(a.trace)[t] = qp;
             }
-            if (flush) continue;
-            double q, mom, g;
+            if (flush) return;
+            double q, mom, g, var = L.var;
             if (is_new) {
                 if (adapt) {   // quadpotential.QuadPotentialDiagAdapt.update with the sample just produced
-                    { const double od = qp - fm; fm += od / fg_w; fr = fma(od, qp - fm, fr); }
-                    { const double od = qp - bm; bm += od / bg_w; br = fma(od, qp - bm, br); }
-                    var = fr / fg_w;
+                    double fm = L.fm, fr = L.fr, bm = L.bm, br = L.br;
+                    welford_add(qp, inv_fg, fm, fr);
+                    welford_add(qp, inv_bg, bm, br);
+                    var = fr * inv_fg;
                     VAR[i] = var;
                     if (sw) { FM[i] = bm; FR[i] = br; BM[i] = 0.0; BR[i] = 0.0; }
                     else { FM[i] = fm; FR[i] = fr; BM[i] = bm; BR[i] = br; }
                 }
-                const unsigned gd = (unsigned)(p.coord_offset + d);
-                const uint4 r = philox4x32_10(make_uint4((unsigned)draw, kPurposeMomentum, gd, (unsigned)(draw >> 32)), key);
-                const double u1 = u01_open(r.x, r.y), u2 = u01_open(r.z, r.w);
-                const double z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
-                mom = z * rsqrt(var);
+                mom = L.z * rsqrt(var);          // p ~ N(0, 1/var); z was drawn ahead of time (slot Z)
                 PL[i] = mom; PR[i] = mom; PST[i] = mom;
                 QL[i] = qp; QR[i] = qp; GL[i] = gp; GR[i] = gp;
                 kin0 = fma(0.5 * var * mom, mom, kin0);
                 q = qp; g = gp;
             } else if (is_first) {
-                if (edge_in_regs && dir == dir_prev) { q = qw; mom = pw; g = gw; }
-                else { q = qe; mom = pe; g = ge; }
+                if (merge && dir == dir_prev) { q = L.qw; mom = L.pw; g = L.gw; }
+                else { q = L.qe; mom = L.pe; g = L.ge; }
             } else {
-                q = qw; mom = pw; g = gw;
+                q = L.qw; mom = L.pw; g = L.gw;
                 if (take) { QS[i] = q; GS[i] = g; }
             }
             const double ph = fma(h, g, mom);
             PW[i] = ph;
             QW[i] = fma(2.0 * h * var, ph, q);
+        };
+        int d = v.r0;
+        for (; d + v.rstep < p.D; d += 2 * v.rstep) {
+            PreLoads L0, L1;
+            load(d, L0);
+            load(d + v.rstep, L1);
+            process(d, L0);
+            process(d + v.rstep, L1);
+        }
+        if (d < p.D) {
+            PreLoads L0;
+            load(d, L0);
+            process(d, L0);
         }
     }
     // kinetic energy of the fresh momenta -> quantity kAqKin0 (fixed-order CTA reduction)
@@ -369,94 +406,225 @@ __device__ __forceinline__ void tick_pre(const AsyncParams& a, unsigned char* sm
 }
 
 // ---- tick, vector part 2: second half kick + per-chain reductions (kinetic, sub-block U-turn dots for
-// the chain's own checkpoint levels, speculative whole-tree dots on the last leaf of a doubling)
-__device__ __forceinline__ void tick_post(const AsyncParams& a, unsigned char* smem_raw)
+// the chain's own checkpoint levels, speculative whole-tree dots on the last leaf of a doubling).
+//
+// Every CTA owns a contiguous block of rows and walks it in tiles of 32 rows x all chains:
+//   core pass   lane <-> chain (the [D][Cp] state arrays are chain-minor: coalesced): half kick, running
+//               p_sum, kinetic and whole-tree dots; {p, p_sum, var} of the tile go to shared memory
+//   level pass  lane <-> row, warp <-> chain (transposed through shared memory): the checkpoints are
+//               chain-major [Cp][level][D], so the store of the chain's new checkpoint (even leaves) and
+//               the loads of the levels it checks (odd leaves) are contiguous 512-byte warp accesses no
+//               matter which level each chain is at; the per-(chain, level) dots are reduced by a
+//               shuffle tree and accumulated in shared memory, tile after tile (fixed order).
+constexpr int kTileRows = 32;
+constexpr int kTickMaxChains = 128;   // shared-memory budget of the post phase
+struct PostLayout {
+    int stride;            // tile row stride in doubles (tpr + 1: conflict-free transposed reads)
+    double* t_mom;         // [kTileRows][stride]
+    double* t_ps;
+    double* t_var;
+    double* l_acc;         // [tpr][2 * kNutsMaxDepth]
+    int4* cmd;             // [tpr] {n_lvl, lvl_min, store_level, running}
+    double* red;           // [3][kLikThreads] (reuses the tile area after the last tile)
+};
+__device__ __forceinline__ PostLayout post_layout(unsigned char* smem_raw, int tpr)
+{
+    PostLayout L;
+    L.stride = tpr + 1;
+    double* base = reinterpret_cast<double*>(smem_raw);
+    L.t_mom = base;
+    L.t_ps = L.t_mom + kTileRows * L.stride;
+    L.t_var = L.t_ps + kTileRows * L.stride;
+    L.l_acc = base + (size_t)3 * kTileRows * (kTickMaxChains + 1);          // fixed offsets: the tile area is
+    L.cmd = reinterpret_cast<int4*>(L.l_acc + (size_t)kTickMaxChains * 2 * kNutsMaxDepth);   // sized for kTickMaxChains
+    L.red = base;
+    return L;
+}
+constexpr size_t kPostSmemBytes = ((size_t)3 * kTileRows * (kTickMaxChains + 1) + (size_t)kTickMaxChains * 2 * kNutsMaxDepth) * sizeof(double) +
+                                  (size_t)kTickMaxChains * sizeof(int4);
+constexpr size_t kZSnapOffset = kPostSmemBytes;   // snapshot of the chains that began a transition (Z refill)
+static_assert(kZSnapOffset + kTickMaxChains * sizeof(int) <= kLikStageBytes, "post-phase shared memory");
+static_assert((size_t)3 * kLikThreads * sizeof(double) <= (size_t)3 * kTileRows * (kTickMaxChains + 1) * sizeof(double), "reduction area inside the tile area");
+
+__device__ __forceinline__ void tick_post(const AsyncParams& a, unsigned char* smem_raw, const PhaseTrace& pt)
 {
     const NutsParams& p = a.n;
-    const TickIdx v = tick_index(p);
-    constexpr int NQ = kAqTree0 + 2;
-    double acc[NQ];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tpr = p.Cp;                       // threads along the chain axis (Cp <= kTickMaxChains)
+    const int rpb = kLikThreads / tpr;          // rows per CTA pass of the core mapping
+    const int c = tid % tpr, rs = tid / tpr;
+    const bool t_on = rs < rpb;
+    const PostLayout L = post_layout(smem_raw, tpr);
+    // ---- per-chain commands of this tick -> shared memory; snapshot for the Z refill (tick_scalar)
+    {
+        int* const s_new = reinterpret_cast<int*>(smem_raw + kZSnapOffset);
+        for (int cc = tid; cc < tpr; cc += kLikThreads) {
+            const bool run = afl(a, kAfPhase, cc) == kPhaseRun;
+            L.cmd[cc] = make_int4(run ? afl(a, kAfNLvl, cc) : 0, afl(a, kAfLvlMin, cc), run ? afl(a, kAfStoreLevel, cc) : -1, run ? 1 : 0);
+            s_new[cc] = (cc < p.C && run && afl(a, kAfNew, cc) != 0) ? afl(a, kAfDraw, cc) + 1 : -1;
+        }
+        for (int o = tid; o < tpr * 2 * kNutsMaxDepth; o += kLikThreads) L.l_acc[o] = 0.0;
+    }
+    const bool on = t_on && afl(a, kAfPhase, c) == kPhaseRun;
+    const int dir = afl(a, kAfDir, c), leaf = afl(a, kAfLeaf, c);
+    const bool last = afl(a, kAfLastLeaf, c) != 0;
+    const double h = sc(p, kScH, c);
+    const double* const VAR = slot(p, kSlotVar);
+    double* const PW = slot(p, kSlotPW);
+    const double* const GW = slot(p, kSlotGW);
+    double* const PSR = slot(p, kSlotPSumRun);
+    const double* const PST = slot(p, kSlotPSumTree);
+    const double* const PO = slot(p, dir > 0 ? kSlotPL : kSlotPR);
+    double a_kin = 0.0, a_t0 = 0.0, a_t1 = 0.0;
+    const int rows_per_cta = (p.D + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int r_begin = (int)blockIdx.x * rows_per_cta;
+    const int r_end = min(p.D, r_begin + rows_per_cta);
+    __syncthreads();
+    stamp(pt, 8);
+    constexpr int U = 4;    // rows per thread and tile at 64 chains (more chains: fewer rows per thread)
+    const int n_u = (kTileRows + rpb - 1) / rpb;             // core rows per thread and tile (<= U for Cp >= 64)
+    const int buf_doubles = 3 * kTileRows * L.stride;
+    double var[U], gwv[U], pwv[U], psr[U], pstv[U], pov[U];
+
+    // core pass, part 1: all global loads of a tile's rows of this thread (kept in registers)
+    auto core_load = [&](int tile0, int u0) {
 #pragma unroll
-    for (int k = 0; k < NQ; ++k) acc[k] = 0.0;
-    const int c = v.chain;
-    const bool on = v.on && afl(a, kAfPhase, c) == kPhaseRun;
-    if (on) {
-        const int dir = afl(a, kAfDir, c), leaf = afl(a, kAfLeaf, c), store_level = afl(a, kAfStoreLevel, c);
-        const int lvl_min = afl(a, kAfLvlMin, c);
-        const int n_lvl = afl(a, kAfNLvl, c);
-        const bool last = afl(a, kAfLastLeaf, c) != 0;
-        const double h = sc(p, kScH, c);
-        const double* const VAR = slot(p, kSlotVar);
-        double* const PW = slot(p, kSlotPW);
-        const double* const GW = slot(p, kSlotGW);
-        double* const PSR = slot(p, kSlotPSumRun);
-        const double* const PST = slot(p, kSlotPSumTree);
-        const double* const PO = slot(p, dir > 0 ? kSlotPL : kSlotPR);
-        for (int d = v.r0; d < p.D; d += v.rstep) {
-            const size_t i = (size_t)d * p.Cp + c;
-            // all loads of this element up front (independent -> one memory round trip per row)
-            const double var = VAR[i], gwv = GW[i], pwv = PW[i];
-            const double psr = (leaf == 0) ? 0.0 : PSR[i];
-            double pstv = 0.0, pov = 0.0;
-            if (last) { pstv = PST[i]; pov = PO[i]; }
-            constexpr int kHoist = BGH_POST_HOIST;  // deeper levels are rare: loaded inline (register budget)
-            double pcv[kHoist > 0 ? kHoist : 1], csv[kHoist > 0 ? kHoist : 1];
-#pragma unroll
-            for (int l = 0; l < kHoist; ++l) {
-                pcv[l] = csv[l] = 0.0;
-                if (l < n_lvl) {
-                    const double2 ck = *ckpt2(p, lvl_min + l, i);
-                    pcv[l] = ck.x;
-                    csv[l] = ck.y;
-                }
-            }
-            const double mom = fma(h, gwv, pwv);
-            PW[i] = mom;
-            const double vel = var * mom;
-            acc[0] = fma(0.5 * vel, mom, acc[0]);
-            const double ps = psr + mom;
-            PSR[i] = ps;
-            if (store_level >= 0) {
-                *ckpt2(p, store_level, i) = make_double2(mom, ps);
-            }
-#pragma unroll
-            for (int l = 0; l < kNutsMaxDepth; ++l) {
-                if (l < n_lvl) {
-                    double pc, cs;
-                    if (l < kHoist) {
-                        pc = pcv[l < kHoist ? l : 0];
-                        cs = csv[l < kHoist ? l : 0];
-                    } else {
-                        const double2 ck = *ckpt2(p, lvl_min + l, i);
-                        pc = ck.x;
-                        cs = ck.y;
-                    }
-                    const double sub = ps - cs + pc;
-                    acc[1 + 2 * l] = fma(sub, var * pc, acc[1 + 2 * l]);
-                    acc[2 + 2 * l] = fma(sub, vel, acc[2 + 2 * l]);
-                }
-            }
-            if (last) {
-                const double pst = pstv + ps;
-                acc[kAqTree0] = fma(pst, vel, acc[kAqTree0]);
-                acc[kAqTree0 + 1] = fma(pst, var * pov, acc[kAqTree0 + 1]);
+        for (int u = 0; u < U; ++u) {
+            const int rt = rs + (u0 + u) * rpb, d = tile0 + rt;
+            var[u] = gwv[u] = pwv[u] = psr[u] = pstv[u] = pov[u] = 0.0;
+            if (on && rt < kTileRows && d < r_end) {
+                const size_t i = (size_t)d * p.Cp + c;
+                var[u] = VAR[i]; gwv[u] = GW[i]; pwv[u] = PW[i];
+                if (leaf != 0) psr[u] = PSR[i];
+                if (last) { pstv[u] = PST[i]; pov[u] = PO[i]; }
             }
         }
-    }
-    // CTA reduction in a fixed order: red[k][thread], then one thread per (quantity, chain)
-    double* const red = reinterpret_cast<double*>(smem_raw);   // NQ * kLikThreads doubles <= staging area
+    };
+    // core pass, part 2: half kick, running p_sum, kinetic / whole-tree dots; tile -> shared memory
+    auto core_compute = [&](int tile0, int u0, int buf) {
+        double* const tm = L.t_mom + buf * buf_doubles;
+        double* const tp = L.t_ps + buf * buf_doubles;
+        double* const tv = L.t_var + buf * buf_doubles;
 #pragma unroll
-    for (int k = 0; k < NQ; ++k) red[k * kLikThreads + threadIdx.x] = acc[k];
+        for (int u = 0; u < U; ++u) {
+            const int rt = rs + (u0 + u) * rpb, d = tile0 + rt;
+            if (t_on && rt < kTileRows) {
+                double mom = 0.0, ps = 0.0;
+                if (on && d < r_end) {
+                    const size_t i = (size_t)d * p.Cp + c;
+                    mom = fma(h, gwv[u], pwv[u]);
+                    PW[i] = mom;
+                    const double vel = var[u] * mom;
+                    a_kin = fma(0.5 * vel, mom, a_kin);
+                    ps = psr[u] + mom;
+                    PSR[i] = ps;
+                    if (last) {
+                        const double pst = pstv[u] + ps;
+                        a_t0 = fma(pst, vel, a_t0);
+                        a_t1 = fma(pst, var[u] * pov[u], a_t1);
+                    }
+                }
+                tm[rt * L.stride + c] = mom;     // rows past the end / idle chains: zeros
+                tp[rt * L.stride + c] = ps;
+                tv[rt * L.stride + c] = var[u];
+            }
+        }
+    };
+    // level pass (lane <-> row of the tile, warp <-> chain): 4 chains per warp and round, the
+    // checkpoint loads of all four in flight together (2 levels hoisted, deeper levels are rare)
+    auto level_pass = [&](int tile0, int buf) {
+        const double* const tm = L.t_mom + buf * buf_doubles;
+        const double* const tp = L.t_ps + buf * buf_doubles;
+        const double* const tv = L.t_var + buf * buf_doubles;
+        const int d = tile0 + lane;
+        const bool row_ok = d < r_end;
+        constexpr int J = BGH_POST_J, HL = BGH_POST_HL;
+        auto reduce_add = [&](int cc, int l, double d0, double d1) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+                d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+            }
+            if (lane == 0) {
+                L.l_acc[cc * 2 * kNutsMaxDepth + 2 * l] += d0;
+                L.l_acc[cc * 2 * kNutsMaxDepth + 2 * l + 1] += d1;
+            }
+        };
+        for (int cc0 = warp; cc0 < tpr; cc0 += J * kLikWarps) {
+            int4 cm[J];
+            double mom[J], ps[J], vr[J];
+            double2 ck[J][HL];
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int cc = cc0 + j * kLikWarps;
+                cm[j] = cc < tpr ? L.cmd[cc] : make_int4(0, 0, -1, 0);
+                mom[j] = ps[j] = vr[j] = 0.0;
+                if (cm[j].w != 0 && (cm[j].x > 0 || cm[j].z >= 0)) {         // warp-uniform
+                    mom[j] = tm[lane * L.stride + cc];
+                    ps[j] = tp[lane * L.stride + cc];
+                    vr[j] = tv[lane * L.stride + cc];
+                    if (cm[j].z >= 0 && row_ok) *ckpt2(p, cm[j].z, d, cc) = make_double2(mom[j], ps[j]);
+                }
+#pragma unroll
+                for (int l = 0; l < HL; ++l) {
+                    ck[j][l] = make_double2(0.0, 0.0);
+                    if (l < cm[j].x && row_ok) ck[j][l] = *ckpt2(p, cm[j].y + l, d, cc);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int cc = cc0 + j * kLikWarps;
+                const double vel = vr[j] * mom[j];
+#pragma unroll
+                for (int l = 0; l < HL; ++l) {
+                    if (l < cm[j].x) {                                       // warp-uniform
+                        const double pc = ck[j][l].x;
+                        const double sub = ps[j] - ck[j][l].y + pc;          // rows past the end: exactly 0
+                        reduce_add(cc, l, sub * (vr[j] * pc), sub * vel);
+                    }
+                }
+                for (int l = HL; l < cm[j].x; ++l) {
+                    double2 k2 = make_double2(0.0, 0.0);
+                    if (row_ok) k2 = *ckpt2(p, cm[j].y + l, d, cc);
+                    const double sub = ps[j] - k2.y + k2.x;
+                    reduce_add(cc, l, sub * (vr[j] * k2.x), sub * vel);
+                }
+            }
+        }
+    };
+
+    // (a software pipeline over the tiles — core loads of tile t+1 in flight during the level pass of tile t,
+    // two tile buffers — was measured slower: it pushes the kernel over the 128-register budget)
+    for (int tile0 = r_begin; tile0 < r_end; tile0 += kTileRows) {
+        for (int u0 = 0; u0 < n_u; u0 += U) {
+            core_load(tile0, u0);
+            core_compute(tile0, u0, 0);
+        }
+        __syncthreads();
+        level_pass(tile0, 0);
+        __syncthreads();
+    }
+    stamp(pt, 9);
+    // ---- CTA reduction of the three core sums in a fixed order, then the partials of this CTA
+    L.red[0 * kLikThreads + tid] = a_kin;
+    L.red[1 * kLikThreads + tid] = a_t0;
+    L.red[2 * kLikThreads + tid] = a_t1;
     __syncthreads();
-    for (int o = threadIdx.x; o < NQ * v.tpr; o += kLikThreads) {
-        const int k = o / v.tpr, cc = o % v.tpr;
+    stamp(pt, 10);
+    for (int o = tid; o < (kAqTree0 + 2) * tpr; o += kLikThreads) {
+        const int k = o / tpr, cc = o % tpr;
         double t = 0.0;
-        for (int r = 0; r < v.rpb; ++r) t += red[k * kLikThreads + r * v.tpr + cc];
+        if (k == 0 || k >= kAqTree0) {
+            const int q = k == 0 ? 0 : 1 + (k - kAqTree0);
+            for (int r = 0; r < rpb; ++r) t += L.red[q * kLikThreads + r * tpr + cc];
+        } else {
+            t = L.l_acc[cc * 2 * kNutsMaxDepth + (k - 1)];
+        }
         p.partials[((size_t)blockIdx.x * kAsyncPartials + k) * p.Cp + cc] = t;
     }
     __syncthreads();
 }
-static_assert((size_t)(kAqTree0 + 2) * kLikThreads * sizeof(double) <= kLikStageBytes, "post-phase reduction area");
+
 
 __device__ __forceinline__ void schedule_leaf_sm(int* fl, int leaf, int depth)
 {
@@ -490,6 +658,23 @@ __device__ __forceinline__ void tick_scalar(const AsyncParams& a, unsigned char*
     int* const s_fl = reinterpret_cast<int*>(s_sc + 32);                 // [kAfCount]
     const int tid = threadIdx.x;
     const int n_blk = (int)gridDim.x;
+    if ((int)blockIdx.x >= p.C || n_blk <= p.C) {
+        // CTAs without a chain of their own (all CTAs if there are more chains than CTAs): draw the
+        // standard normals of the NEXT momentum refresh of every chain that began a transition this tick
+        // into slot Z (Philox is counter based: the values do not depend on who computes them or when)
+        const int* const s_new = reinterpret_cast<const int*>(smem_raw + kZSnapOffset);
+        double* const Z = slot(p, kSlotZ);
+        const int first = n_blk > p.C ? p.C : 0, n_help = n_blk - first;
+        const int gtid = ((int)blockIdx.x - first) * kLikThreads + tid, gn = n_help * kLikThreads;
+        for (int cc = 0; cc < p.C; ++cc) {
+            const int draw = s_new[cc];
+            if (draw < 0 || draw >= a.tune + a.draws) continue;      // CTA-uniform
+            const uint2 key = chain_key(p, cc);
+            for (int d = gtid; d < p.D; d += gn)
+                Z[(size_t)d * p.Cp + cc] = momentum_normal(key, draw, (unsigned)(p.coord_offset + d));
+        }
+        __syncthreads();   // the snapshot / reduction area is reused below
+    }
     for (int c = blockIdx.x; c < p.C; c += n_blk) {
         int phase = afl(a, kAfPhase, c);
         if (phase == kPhaseFinished) continue;                           // CTA-uniform
@@ -691,14 +876,15 @@ __global__ void __launch_bounds__(kLikThreads, 1) nuts_tick_kernel(const TickPar
     const FusedParams& f = t.f;
     unsigned long long target = f.bar_base;
     for (int tick = 0; tick < t.n_ticks; ++tick) {
-#define BGH_PHASE_STAMP(k)                                                                              \
-    do {                                                                                                \
-        const int gt_ = t.tick_base + tick - t.trace_first;                                             \
-        if (t.phase_trace != nullptr && threadIdx.x == 0 && gt_ >= 0 && gt_ < 16)                       \
-            t.phase_trace[((size_t)gt_ * gridDim.x + blockIdx.x) * 8 + (k)] = global_timer_ns();        \
-    } while (0)
+        PhaseTrace pt;
+        pt.buf = t.phase_trace;
+        {
+            const int gt_ = t.tick_base + tick - t.trace_first;
+            pt.row = (gt_ >= 0 && gt_ < 8) ? gt_ * (int)gridDim.x + (int)blockIdx.x : -1;
+        }
+#define BGH_PHASE_STAMP(k) stamp(pt, k)
         BGH_PHASE_STAMP(0);
-        tick_pre(t.a, smem_raw);
+        tick_pre(t.a, smem_raw, pt);
         BGH_PHASE_STAMP(1);
         grid_barrier(f.bar, target, f.status);
         fence_proxy_async();   // the staging area was written through the generic proxy (reductions)
@@ -709,7 +895,7 @@ __global__ void __launch_bounds__(kLikThreads, 1) nuts_tick_kernel(const TickPar
         fin_phase(f.fin, smem_raw);
         BGH_PHASE_STAMP(4);
         grid_barrier(f.bar, target, f.status);
-        tick_post(t.a, smem_raw);
+        tick_post(t.a, smem_raw, pt);
         BGH_PHASE_STAMP(5);
         grid_barrier(f.bar, target, f.status);
         BGH_PHASE_STAMP(6);

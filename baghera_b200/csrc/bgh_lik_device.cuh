@@ -47,10 +47,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+// The SNP stream is read exactly once per evaluation while the kernel is FP64-bound: mark it evict-first
+// in L2 so that it does not push the sampler state (which IS re-read every tick) out of the 126 MB L2.
+__device__ __forceinline__ unsigned long long l2_evict_first_policy()
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, unsigned long long pol)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(pol)
                  : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
@@ -173,6 +181,7 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
 
     const int base0 = ra & ~(CH - 1);   // CH aligned: every bulk copy source is 16-byte aligned
     const int n_chunks = active ? (rb - base0 + CH - 1) / CH : 0;
+    const unsigned long long pol = l2_evict_first_policy();
     auto issue = [&](int k) {   // lane lc == 0 of the group
         const int st = k & (kStages - 1);
         const size_t b0 = (size_t)base0 + (size_t)k * CH;
@@ -181,10 +190,10 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
         const uint32_t d_s = smem_u32(reinterpret_cast<double*>(sb) + grp * (CH + 2));
         const uint32_t d_g = smem_u32(reinterpret_cast<int*>(reinterpret_cast<double*>(sb) + 3 * kStride) + grp * (CH + 4));
         mbar_expect_tx(bar, CH * 28);
-        bulk_g2s(d_s, p.sp + b0, CH * 8, bar);
-        bulk_g2s(d_s + kStride * 8, p.wp + b0, CH * 8, bar);
-        bulk_g2s(d_s + 2 * kStride * 8, p.lp + b0, CH * 8, bar);
-        bulk_g2s(d_g, p.gid + b0, CH * 4, bar);
+        bulk_g2s(d_s, p.sp + b0, CH * 8, bar, pol);
+        bulk_g2s(d_s + kStride * 8, p.wp + b0, CH * 8, bar, pol);
+        bulk_g2s(d_s + 2 * kStride * 8, p.lp + b0, CH * 8, bar, pol);
+        bulk_g2s(d_g, p.gid + b0, CH * 4, bar, pol);
     };
     if (lc == 0) {
         if (n_chunks > 0) issue(0);

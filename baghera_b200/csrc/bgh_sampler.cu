@@ -125,10 +125,7 @@ __global__ void __launch_bounds__(kVecThreads) nuts_begin_kernel(const NutsParam
         for (int d = v.r0; d < p.D; d += v.rstep) {
             const size_t i = (size_t)d * p.Cp + v.chain;
             // one normal per (coordinate, chain): Box-Muller on a Philox block keyed by the GLOBAL coordinate
-            const unsigned gd = (unsigned)(p.coord_offset + d);
-            const uint4 r = philox4x32_10(make_uint4((unsigned)p.draw, kPurposeMomentum, gd, (unsigned)(p.draw >> 32)), key);
-            const double u1 = u01_open(r.x, r.y), u2 = u01_open(r.z, r.w);
-            const double z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+            const double z = momentum_normal(key, p.draw, (unsigned)(p.coord_offset + d));
             const double var = VAR[i];
             const double mom = z * rsqrt(var);          // p ~ N(0, 1/var)   (quadpotential.random)
             P_L[i] = mom;
@@ -247,11 +244,11 @@ __global__ void __launch_bounds__(kVecThreads) nuts_leap2_kernel(const NutsParam
             const double ps = (leaf == 0) ? mom : PSR[i] + mom;
             PSR[i] = ps;
             if (store_level >= 0) {
-                *ckpt2(p, store_level, i) = make_double2(mom, ps);
+                *ckpt2(p, store_level, d, v.chain) = make_double2(mom, ps);
             }
 #pragma unroll
             for (int l = 0; l < NL; ++l) {
-                const double2 ck = *ckpt2(p, lvl_min + l, i);
+                const double2 ck = *ckpt2(p, lvl_min + l, d, v.chain);
                 const double pc = ck.x;
                 const double sub = ps - ck.y + pc;   // p_sum of the aligned block
                 acc[1 + 2 * l] = fma(sub, var * pc, acc[1 + 2 * l]);       // . v_left
@@ -423,21 +420,14 @@ __global__ void __launch_bounds__(kVecThreads) nuts_adapt_mass_kernel(const Nuts
     double* const FR = slot(p, kSlotFgRaw);
     double* const BM = slot(p, kSlotBgMean);
     double* const BR = slot(p, kSlotBgRaw);
+    const double inv_fg = 1.0 / fg_w, inv_bg = 1.0 / bg_w;
     for (int d = v.r0; d < p.D; d += v.rstep) {
         const size_t i = (size_t)d * p.Cp + c;
         const double x = QP[i];
         double fm = FM[i], fr = FR[i], bm = BM[i], br = BR[i];
-        {
-            const double od = x - fm;
-            fm += od / fg_w;                 // fg_w, bg_w are the weights AFTER adding this sample
-            fr = fma(od, x - fm, fr);
-        }
-        {
-            const double od = x - bm;
-            bm += od / bg_w;
-            br = fma(od, x - bm, br);
-        }
-        VAR[i] = fr / fg_w;
+        welford_add(x, inv_fg, fm, fr);      // fg_w, bg_w are the weights AFTER adding this sample
+        welford_add(x, inv_bg, bm, br);
+        VAR[i] = fr * inv_fg;
         if (switch_window) {
             FM[i] = bm; FR[i] = br;
             BM[i] = 0.0; BR[i] = 0.0;
@@ -650,8 +640,22 @@ __global__ void nuts_async_init_kernel(const AsyncParams a, double step0, double
     if (c == 0) *a.n_finished = 0;
 }
 
+// standard normals of every running chain's FIRST transition -> slot Z (later transitions: the tick
+// kernel refills Z cooperatively, see tick_post in bgh_fused.cu)
+__global__ void nuts_async_zgen_kernel(const AsyncParams a)
+{
+    const NutsParams& p = a.n;
+    double* const Z = slot(p, kSlotZ);
+    const size_t n = (size_t)p.D * p.Cp;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int d = (int)(i / p.Cp), c = (int)(i % p.Cp);
+        Z[i] = momentum_normal(chain_key(p, c), 0, (unsigned)(p.coord_offset + d));
+    }
+}
+
 cudaError_t nuts_async_launch_init(const AsyncParams& a, double step0, double initial_weight, cudaStream_t s)
 {
+    nuts_async_zgen_kernel<<<a.n.n_vec_blocks, 256, 0, s>>>(a);
     nuts_async_init_kernel<<<(a.n.Cp + 127) / 128, 128, 0, s>>>(a, step0, initial_weight);
     return cudaGetLastError();
 }

@@ -18,10 +18,11 @@ enum : int {
     kSlotPSumTree, kSlotPSumRun,
     kSlotFgMean = BGH_NUTS_SLOT_FG_MEAN, kSlotFgRaw = BGH_NUTS_SLOT_FG_RAW,
     kSlotBgMean = BGH_NUTS_SLOT_BG_MEAN, kSlotBgRaw = BGH_NUTS_SLOT_BG_RAW,
+    kSlotZ,             // async machine: standard normals of the chain's NEXT momentum refresh
     kSlotCount = BGH_NUTS_N_SLOTS
 };
 static_assert(kSlotPSumRun + 1 == kSlotFgMean, "slot numbering");
-static_assert(kSlotBgRaw + 1 == kSlotCount, "slot numbering");
+static_assert(kSlotZ + 1 == kSlotCount, "slot numbering");
 
 // per-chain scalars sc[k][Cp]
 enum : int {

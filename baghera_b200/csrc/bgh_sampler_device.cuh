@@ -38,6 +38,23 @@ __device__ __forceinline__ uint2 chain_key(const NutsParams& p, int chain)
 }
 enum : unsigned { kPurposeMomentum = 1, kPurposeDir = 2, kPurposeLeaf = 3, kPurposeTop = 4 };
 
+// one standard normal per (chain, draw, GLOBAL coordinate): Box-Muller on a Philox block
+__device__ __forceinline__ double momentum_normal(const uint2 key, long long draw, unsigned global_coord)
+{
+    const uint4 r = philox4x32_10(make_uint4((unsigned)draw, kPurposeMomentum, global_coord, (unsigned)(draw >> 32)), key);
+    const double u1 = u01_open(r.x, r.y), u2 = u01_open(r.z, r.w);
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+// quadpotential._WeightedVariance.add_sample with the weight AFTER adding the sample given as its
+// reciprocal (one division per chain and transition instead of three per coordinate)
+__device__ __forceinline__ void welford_add(double x, double inv_w, double& mean, double& raw)
+{
+    const double od = x - mean;
+    mean = fma(od, inv_w, mean);
+    raw = fma(od, x - mean, raw);
+}
+
 __device__ __forceinline__ double chain_uniform(const NutsParams& p, int chain, unsigned purpose, unsigned idx)
 {
     const uint4 r = philox4x32_10(make_uint4((unsigned)p.draw, purpose, idx, (unsigned)(p.draw >> 32)), chain_key(p, chain));
@@ -54,12 +71,13 @@ __device__ __forceinline__ double logaddexp_d(double a, double b)
 
 // vector slot accessor: state is [n_slots][D][Cp]
 __device__ __forceinline__ double* slot(const NutsParams& p, int s) { return p.state + (size_t)s * p.D * p.Cp; }
-// checkpoints: [D][Cp][kNutsMaxDepth] pairs {p, running p_sum} — the levels of one (coordinate, chain)
-// are contiguous, so chains that sit at different tree positions still read / write whole 16-byte pairs
-// (consecutive levels share a 32-byte sector) instead of one sector per value.
-__device__ __forceinline__ double2* ckpt2(const NutsParams& p, int level, size_t i)
+// checkpoints: chain-major [Cp][kNutsMaxDepth][D] pairs {p, running p_sum}.  One (chain, level) is a
+// contiguous stream over the coordinates, so the tick kernel — which transposes a tile of rows through
+// shared memory — reads and writes checkpoints fully coalesced even though every chain sits at its own
+// tree position (its own level).
+__device__ __forceinline__ double2* ckpt2(const NutsParams& p, int level, int d, int c)
 {
-    return reinterpret_cast<double2*>(p.ckpt) + i * kNutsMaxDepth + level;
+    return reinterpret_cast<double2*>(p.ckpt) + ((size_t)c * kNutsMaxDepth + level) * p.D + d;
 }
 __device__ __forceinline__ double& sc(const NutsParams& p, int k, int c) { return p.sc[(size_t)k * p.Cp + c]; }
 __device__ __forceinline__ int& fl(const NutsParams& p, int k, int c) { return p.fl[(size_t)k * p.Cp + c]; }

@@ -171,7 +171,7 @@ int bgh_debug_plan(int64_t M, const int32_t* gid_sorted, int32_t G, int32_t n_ct
  * ------------------------------------------------------------------------------------------ */
 #define BGH_NUTS_MAX_DEPTH 10
 #define BGH_NUTS_MAX_PARTIALS (1 + 2 * BGH_NUTS_MAX_DEPTH)
-#define BGH_NUTS_N_SLOTS 20
+#define BGH_NUTS_N_SLOTS 21
 #define BGH_NUTS_SLOT_Q 0
 #define BGH_NUTS_SLOT_GRAD 1
 #define BGH_NUTS_SLOT_VAR 2

@@ -22,9 +22,9 @@ n_cta = 148
 words = eng.Cp // 64 * n_cta * 16 * 8 if eng.Cp >= 64 else n_cta * 16 * 8
 buf = np.zeros(words, dtype=np.uint64)
 check(eng.L.bgh_debug_trace(eng.ctx, 1, buf.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), words), eng.ctx)
-t = buf[:16 * n_cta * 8].reshape(16, n_cta, 8).astype(np.int64)
+t = buf[:8 * n_cta * 16].reshape(8, n_cta, 16).astype(np.int64)
 names = ["pre", "barrier1", "lik", "barrier2+fin", "barrier3+post", "barrier4", "scalar", "barrier5"]
-for tick in (1, 6, 12):
+for tick in (1, 3, 6):
     tt = t[tick] - t[tick].min()
     print("tick", tick)
     for k in range(8):
@@ -32,4 +32,9 @@ for tick in (1, 6, 12):
         dur = (nxt - t[tick, :, k]) / 1e3
         print("  %-14s start p50 %7.2f  dur min %6.2f p50 %6.2f max %6.2f us" % (names[k], np.median(tt[:, k]) / 1e3, dur.min(), np.median(dur), dur.max()))
     print("  tick total %.2f us" % ((t[tick + 1, 0, 0] - t[tick, 0, 0]) / 1e3))
+    sub = ["post: barrier3 + Z refill", "post: core rows", "post: level dots", "post: CTA reduce"]
+    marks = [t[tick, :, 4], t[tick, :, 8], t[tick, :, 9], t[tick, :, 10], t[tick, :, 5]]
+    for k in range(4):
+        dur = (marks[k + 1] - marks[k]) / 1e3
+        print("    %-26s dur min %6.2f p50 %6.2f max %6.2f us" % (sub[k], dur.min(), np.median(dur), dur.max()))
 eng.close()
