@@ -15,7 +15,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 BGH_ABI_VERSION = 1
 BGH_OK, BGH_EINVAL, BGH_ECUDA, BGH_ENOMEM, BGH_ESTATE, BGH_ENODEV = 0, -1, -2, -3, -4, -5
-BGH_MODEL_GENE_NORMAL, BGH_MODEL_GW_NORMAL = 0, 1
+BGH_MODEL_GENE_NORMAL, BGH_MODEL_GW_NORMAL, BGH_MODEL_GENE_GAMMA = 0, 1, 2
 
 
 class BghError(RuntimeError):
@@ -41,7 +41,9 @@ class bgh_cfg(ctypes.Structure):
         ("last_gene_row", ctypes.c_int32),
         ("n_shared_rows", ctypes.c_int32),
         ("sm_count_override", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 5),
+        ("reserved0", ctypes.c_int32),
+        ("gamma_rate", ctypes.c_double),
+        ("reserved", ctypes.c_int32 * 2),
     ]
 
 
@@ -99,6 +101,11 @@ SIGNATURES = {
     "bgh_logp_grad": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "bgh_logp_grad_local": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "bgh_logp_grad_finish": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "bgh_peer_handle_bytes": (_i32, []),
+    "bgh_peer_export": (_i32, [_vp, _vp]),
+    "bgh_peer_connect": (_i32, [_vp, _i32, _i32, _vp]),
+    "bgh_logp_grad_sharded": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "bgh_peer_status": (_i32, [_vp, _pi32]),
     "bgh_logp_grad_host": (_i32, [_vp, _vp, _vp, _vp]),
     "bgh_logp_grad_host_stream": (_i32, [_vp, _i32, _vp, _vp, _vp]),
     "bgh_to_device_layout": (_i32, [_vp, _vp, _vp, _vp]),

@@ -289,6 +289,11 @@ struct bgh_ctx {
     int* d_ticks = nullptr;
     int* h_poll = nullptr;                   // pinned: {n_finished, status, ticks}
     bool fused = true;                       // BGH_UNFUSED=1 -> separate likelihood / finalize launches
+    // peer-memory exchange of sharded contexts (bgh_peer_export / bgh_peer_connect)
+    unsigned char* d_mailbox = nullptr;      // [flags 2 x kMaxPeers x 128 B][mail 2 x kMaxPeers x n doubles]
+    unsigned char* peer_base[kMaxPeers] = {nullptr};
+    int peer_rank = -1, peer_world = 0;
+    unsigned long long peer_epoch = 0;
     // host-entry staging (lazily allocated)
     static constexpr int kPipe = 2;
     double* d_q_cd[kPipe] = {nullptr, nullptr};
@@ -372,8 +377,12 @@ int bgh_create(bgh_ctx** out, const bgh_cfg* cfg)
     if (cfg->abi_version != BGH_ABI_VERSION) return fail(nullptr, BGH_EINVAL, "bgh_create: ABI version mismatch");
     if (cfg->n_snps <= 0 || cfg->n_snps > 0x7fffff00LL) return fail(nullptr, BGH_EINVAL, "bgh_create: n_snps out of range");
     if (cfg->n_chains <= 0 || cfg->n_chains > 4096) return fail(nullptr, BGH_EINVAL, "bgh_create: n_chains out of range");
-    if (cfg->model != BGH_MODEL_GENE_NORMAL && cfg->model != BGH_MODEL_GW_NORMAL)
+    if (cfg->model != BGH_MODEL_GENE_NORMAL && cfg->model != BGH_MODEL_GW_NORMAL && cfg->model != BGH_MODEL_GENE_GAMMA)
         return fail(nullptr, BGH_EINVAL, "bgh_create: unknown model");
+    if (cfg->model == BGH_MODEL_GENE_GAMMA && (!(cfg->gamma_rate > 0.0) || !isfinite(cfg->gamma_rate)))
+        return fail(nullptr, BGH_EINVAL, "bgh_create: the gamma model needs gamma_rate = N_1kG > 0");
+    if (cfg->model == BGH_MODEL_GENE_GAMMA && cfg->n_shared_rows != 0)
+        return fail(nullptr, BGH_EINVAL, "bgh_create: the gamma model runs on single-rank contexts");
     if (cfg->n_genes <= 0 || (cfg->model == BGH_MODEL_GW_NORMAL && cfg->n_genes != 1))
         return fail(nullptr, BGH_EINVAL, "bgh_create: bad n_genes");
     if (!(cfg->c > 0.0) || !isfinite(cfg->c)) return fail(nullptr, BGH_EINVAL, "bgh_create: c must be positive");
@@ -390,7 +399,7 @@ int bgh_create(bgh_ctx** out, const bgh_cfg* cfg)
     if (!ctx) return fail(nullptr, BGH_ENOMEM, "bgh_create: out of host memory");
     ctx->cfg = *cfg;
     if (ctx->cfg.n_genes_total <= 0) ctx->cfg.n_genes_total = cfg->n_genes;
-    ctx->D = (cfg->model == BGH_MODEL_GENE_NORMAL) ? cfg->n_genes + 3 : 2;
+    ctx->D = (cfg->model == BGH_MODEL_GENE_NORMAL) ? cfg->n_genes + 3 : (cfg->model == BGH_MODEL_GENE_GAMMA ? cfg->n_genes + 2 : 2);
     pick_chain_geometry(cfg->n_chains, &ctx->CL, &ctx->CPL, &ctx->Cp);
     ctx->chain_blocks = ctx->Cp / (ctx->CL * ctx->CPL);
 
@@ -438,6 +447,9 @@ void bgh_destroy(bgh_ctx* ctx)
     cudaFree(ctx->d_trace);
     cudaFree(ctx->d_bar); cudaFree(ctx->d_status); cudaFree(ctx->d_ticks);
     if (ctx->h_poll) cudaFreeHost(ctx->h_poll);
+    for (int r = 0; r < kMaxPeers; ++r)
+        if (ctx->peer_base[r] && r != ctx->peer_rank) cudaIpcCloseMemHandle(ctx->peer_base[r]);
+    cudaFree(ctx->d_mailbox);
     cudaFree(ctx->d_split_gene); cudaFree(ctx->d_split_row); cudaFree(ctx->d_split_ptr); cudaFree(ctx->d_split_slots);
     for (int i = 0; i < bgh_ctx::kPipe; ++i) {
         cudaFree(ctx->d_q_cd[i]); cudaFree(ctx->d_q_dc[i]); cudaFree(ctx->d_g_dc[i]); cudaFree(ctx->d_g_cd[i]);
@@ -632,13 +644,13 @@ static void fill_params(bgh_ctx* ctx, const double* q, double* grad, double* log
     lp->sp = ctx->d_xs; lp->wp = ctx->d_xw; lp->lp = ctx->d_xl; lp->gid = ctx->d_gid; lp->groups = ctx->d_groups;
     lp->q = q; lp->grad = grad; lp->slots = ctx->d_slots; lp->part = ctx->d_part; lp->cc = ctx->d_cc; lp->trace = ctx->d_trace;
     lp->Cp = ctx->Cp; lp->G = ctx->cfg.n_genes; lp->NG = ctx->n_groups; lp->n_cta = ctx->n_cta; lp->model = ctx->cfg.model;
-    lp->fix = ctx->cfg.fix_intercept; lp->c = ctx->cfg.c;
+    lp->fix = ctx->cfg.fix_intercept; lp->c = ctx->cfg.c; lp->gamma_rate = ctx->cfg.gamma_rate;
     fp->q = q; fp->grad = grad; fp->logp = logp; fp->slots = ctx->d_slots; fp->part = ctx->d_part; fp->cc = ctx->d_cc;
     fp->payload = payload;
     fp->split_gene = ctx->d_split_gene; fp->split_row = ctx->d_split_row; fp->split_ptr = ctx->d_split_ptr;
     fp->split_slots = ctx->d_split_slots; fp->n_split = (int)ctx->plan.split_gene.size(); fp->n_long = ctx->plan.n_long;
     fp->n_cta = ctx->n_cta; fp->Cp = ctx->Cp; fp->G_total = ctx->cfg.n_genes_total; fp->model = ctx->cfg.model;
-    fp->fix = ctx->cfg.fix_intercept; fp->finish_inline = 0; fp->c = ctx->cfg.c; fp->lik_const = ctx->lik_const;
+    fp->fix = ctx->cfg.fix_intercept; fp->finish_inline = 0; fp->c = ctx->cfg.c; fp->lik_const = ctx->lik_const; fp->gamma_rate = ctx->cfg.gamma_rate;
     fp->first_gene_row = ctx->cfg.first_gene_row; fp->last_gene_row = ctx->cfg.last_gene_row;
     fp->G_local = ctx->cfg.n_genes;
 }
@@ -850,6 +862,102 @@ int bgh_dfma_peak(bgh_ctx* ctx, double* ginstr_per_s)
     cudaEventDestroy(e1);
     cudaFree(d_out);
     *ginstr_per_s = best;
+    return BGH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sharded evaluation with the payload all-reduce fused into the kernel (peer-mapped mailboxes)
+// ---------------------------------------------------------------------------------------------
+static constexpr size_t kFlagBytes = 2 * (size_t)kMaxPeers * 128;
+static size_t mailbox_bytes(const bgh_ctx* ctx)
+{
+    return kFlagBytes + 2 * (size_t)kMaxPeers * (size_t)(4 + ctx->cfg.n_shared_rows) * ctx->Cp * sizeof(double);
+}
+
+int32_t bgh_peer_handle_bytes(void) { return (int32_t)sizeof(cudaIpcMemHandle_t); }
+
+int bgh_peer_export(bgh_ctx* ctx, void* handle_out)
+{
+    if (!ctx || !handle_out) return fail(ctx, BGH_EINVAL, "bgh_peer_export: null argument");
+    if (!ctx->uploaded) return fail(ctx, BGH_ESTATE, "bgh_peer_export: call bgh_upload first");
+    BGH_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    if (!ctx->d_mailbox) {
+        BGH_CUDA(ctx, cudaMalloc(&ctx->d_mailbox, mailbox_bytes(ctx)));
+        BGH_CUDA(ctx, cudaMemset(ctx->d_mailbox, 0, mailbox_bytes(ctx)));
+        BGH_CUDA(ctx, cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    BGH_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->d_mailbox));
+    memcpy(handle_out, &h, sizeof(h));
+    return BGH_OK;
+}
+
+int bgh_peer_connect(bgh_ctx* ctx, int32_t rank, int32_t world, const void* handles)
+{
+    if (!ctx || !handles || world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+        return fail(ctx, BGH_EINVAL, "bgh_peer_connect: bad argument (at most 8 ranks)");
+    if (!ctx->d_mailbox) return fail(ctx, BGH_ESTATE, "bgh_peer_connect: call bgh_peer_export first");
+    BGH_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            ctx->peer_base[r] = ctx->d_mailbox;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const unsigned char*)handles + (size_t)r * sizeof(h), sizeof(h));
+        void* ptr = nullptr;
+        BGH_CUDA(ctx, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_base[r] = (unsigned char*)ptr;
+    }
+    ctx->peer_rank = rank;
+    ctx->peer_world = world;
+    ctx->peer_epoch = 0;
+    return BGH_OK;
+}
+
+int bgh_logp_grad_sharded(bgh_ctx* ctx, const double* q, double* logp, double* grad, void* stream)
+{
+    if (!ctx || !q || !logp || !grad) return fail(ctx, BGH_EINVAL, "bgh_logp_grad_sharded: null argument");
+    if (!ctx->uploaded) return fail(ctx, BGH_ESTATE, "bgh_logp_grad_sharded: call bgh_upload first");
+    if (ctx->peer_world < 1) return fail(ctx, BGH_ESTATE, "bgh_logp_grad_sharded: call bgh_peer_connect first");
+    if (!ctx->fused) return fail(ctx, BGH_ESTATE, "bgh_logp_grad_sharded: needs the cooperative kernels");
+    LikParams lp;
+    FinParams fp;
+    fill_params(ctx, q, grad, logp, ctx->d_payload, &lp, &fp);
+    fp.finish_inline = 0;
+    FusedParams f;
+    f.lik = lp; f.fin = fp; f.bar = ctx->d_bar; f.status = ctx->d_status; f.chain_blocks = ctx->chain_blocks;
+    f.bar_base = ctx->bar_count;
+    ctx->bar_count += 2ull * (unsigned long long)ctx->n_cta;   // two grid barriers per launch
+    PeerParams pr;
+    memset(&pr, 0, sizeof(pr));
+    for (int r = 0; r < ctx->peer_world; ++r) {
+        pr.flag[r] = reinterpret_cast<unsigned long long*>(ctx->peer_base[r]);
+        pr.mail[r] = reinterpret_cast<double*>(ctx->peer_base[r] + kFlagBytes);
+    }
+    pr.rank = ctx->peer_rank; pr.world = ctx->peer_world;
+    pr.n = (4 + ctx->cfg.n_shared_rows) * ctx->Cp;
+    pr.epoch = ++ctx->peer_epoch;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaEvent_t* ev = nullptr;
+    if (ctx->profiling && ctx->prof_n < bgh_ctx::kProfCap) {
+        ev = &ctx->prof_ev[3 * ctx->prof_n];
+        ctx->prof_n++;
+        BGH_CUDA(ctx, cudaEventRecord(ev[0], s));
+    }
+    BGH_CUDA(ctx, launch_logp_grad_sharded(f, pr, ctx->CL, ctx->CPL, ctx->n_cta, s));
+    if (ev) {
+        BGH_CUDA(ctx, cudaEventRecord(ev[1], s));
+        BGH_CUDA(ctx, cudaEventRecord(ev[2], s));
+    }
+    ctx->launches += 1;
+    return BGH_OK;
+}
+
+int bgh_peer_status(bgh_ctx* ctx, int32_t* status)
+{
+    if (!ctx || !status) return BGH_EINVAL;
+    BGH_CUDA(ctx, cudaMemcpy(status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost));
     return BGH_OK;
 }
 

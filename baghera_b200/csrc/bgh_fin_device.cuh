@@ -14,6 +14,22 @@ namespace bgh {
 // per-chain closing formulas (priors, transforms, Jacobians) — ref: gene_regression.py:78-81,
 // heritability.py:45-49; PyMC3 3.6 distributions/continuous.py + transforms.py
 // ---------------------------------------------------------------------------------------------
+// digamma for x > 0: recurrence up to x >= 10, then the asymptotic series (|error| < 1e-15 relative)
+__device__ __forceinline__ double digamma_d(double x)
+{
+    double r = 0.0;
+    while (x < 10.0) {
+        r -= 1.0 / x;
+        x += 1.0;
+    }
+    const double f = 1.0 / (x * x);
+    const double t = f * (-1.0 / 12.0 + f * (1.0 / 120.0 + f * (-1.0 / 252.0 + f * (1.0 / 240.0 + f * (-1.0 / 132.0 +
+                     f * (691.0 / 32760.0 + f * (-1.0 / 12.0)))))));
+    return r + log(x) - 0.5 / x + t;
+}
+
+constexpr double kGammaETau = 1.0e6;   // e ~ Normal(1, sd=0.001), ref: gene_regression.py:229
+
 struct ChainSums {
     double A_ll, A_e, S1, S2;
 };
@@ -29,6 +45,26 @@ __device__ __forceinline__ ChainConst chain_const(const FinParams& p, int ch)
 {
     const int Cp = p.Cp;
     ChainConst c;
+    if (p.model == BGH_MODEL_GENE_GAMMA) {
+        // ref: gene_regression.py:229-231.  e ~ Normal(1, 0.001); mi ~ Beta(1,1) (logodds);
+        // beta_g ~ Gamma(alpha = mi, beta = rate) sampled as beta_log__:
+        //   sum_g [ -lgamma(mi) + mi log(rate) - rate beta_g + (mi - 1) x_g + x_g ]   (x_g = log beta_g, Jacobian x_g)
+        const double e = p.q[0 * Cp + ch], xm = p.q[1 * Cp + ch];
+        const double ax = fabs(xm);
+        const double u = exp(-ax);
+        const double L = log1p(u);
+        c.mi = (xm >= 0.0 ? 1.0 : u) / (1.0 + u);
+        const double G = (double)p.G_total;
+        const double lrate = log(p.gamma_rate);
+        double lp = -0.5 * kGammaETau * (e - 1.0) * (e - 1.0) + 0.5 * (log(kGammaETau) - kLog2Pi);
+        lp += -ax - 2.0 * L;                                       // Beta(1,1)=0 ; logodds Jacobian
+        lp += G * (-lgamma(c.mi) + c.mi * lrate);
+        lp += p.lik_const;
+        c.lp0 = lp;
+        c.iW = G * (lrate - digamma_d(c.mi));                      // d/d mi of the gene-independent prior terms
+        c.iW2 = 0.0;
+        return c;
+    }
     if (p.model == BGH_MODEL_GENE_NORMAL) {
         const double xW = p.q[0 * Cp + ch], e = p.q[1 * Cp + ch], xm = p.q[2 * Cp + ch];
         const double ax = fabs(xm);
@@ -73,6 +109,14 @@ __device__ __forceinline__ ChainConst chain_const(const FinParams& p, int ch)
 __device__ __forceinline__ void finish_chain(const FinParams& p, int ch, const ChainSums& s, const ChainConst& c)
 {
     const int Cp = p.Cp;
+    if (p.model == BGH_MODEL_GENE_GAMMA) {
+        // S1 = sum_g x_g, S2 = sum_g beta_g (owned genes)
+        const double e = p.q[0 * Cp + ch];
+        p.logp[ch] = c.lp0 + c.mi * s.S1 - p.gamma_rate * s.S2 - 0.5 * s.A_ll;
+        p.grad[0 * Cp + ch] = -kGammaETau * (e - 1.0) + (p.fix ? 0.0 : s.A_e);
+        p.grad[1 * Cp + ch] = 1.0 - 2.0 * c.mi + c.mi * (1.0 - c.mi) * (c.iW + s.S1);
+        return;
+    }
     if (p.model == BGH_MODEL_GENE_NORMAL) {
         const double e = p.q[1 * Cp + ch];
         const double G = (double)p.G_total;
@@ -105,13 +149,16 @@ __device__ __forceinline__ GeneCoef load_gene_coef(const FinParams& p, int gene,
         gc.iW2 = p.cc[0 * p.Cp + ch];
         gc.mi = p.cc[1 * p.Cp + ch];
         if (p.model == BGH_MODEL_GENE_NORMAL) gc.beta = p.q[(size_t)(3 + gene) * p.Cp + ch];
+        if (p.model == BGH_MODEL_GENE_GAMMA) gc.beta = exp(p.q[(size_t)(2 + gene) * p.Cp + ch]);
     }
     return gc;
 }
 __device__ __forceinline__ void finish_gene(const FinParams& p, int gene, int ch, double sum_r, const GeneCoef& gc)
 {
     const int Cp = p.Cp;
-    if (p.model == BGH_MODEL_GENE_NORMAL) {
+    if (p.model == BGH_MODEL_GENE_GAMMA) {
+        p.grad[(size_t)(2 + gene) * Cp + ch] = fma(gc.beta, fma(p.c, sum_r, -p.gamma_rate), gc.mi);
+    } else if (p.model == BGH_MODEL_GENE_NORMAL) {
         p.grad[(size_t)(3 + gene) * Cp + ch] = fma(p.c, sum_r, -(gc.beta - gc.mi) * gc.iW2);
     } else {
         // (c*sum_r - 1/(1-mi)) * mi(1-mi) + (1 - 2mi)

@@ -226,6 +226,100 @@ __global__ void __launch_bounds__(kLikThreads, 1) logp_grad_fused_kernel(const F
 }
 
 // ---------------------------------------------------------------------------------------------
+// sharded evaluation: likelihood pass | finalize (payload) | ONE-SHOT ALL-REDUCE over peer memory | finish,
+// all inside one launch per rank.  The payload ([4 + shared genes][Cp] fp64, a few KB) is latency bound:
+// instead of a separate NCCL launch, CTA 0 stores its payload straight into every peer's mailbox over
+// NVLink, releases a system-scope flag, waits for the peers' flags and adds the R contributions in RANK
+// ORDER (every rank obtains bit-identical totals, hence identical NUTS decisions).  Mailboxes are
+// double buffered by launch parity: a rank can only be one launch ahead of its slowest peer, because it
+// needs that peer's flag of launch e to finish launch e.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p)
+{
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// executed by one whole CTA; on return payload[0..n) holds the rank-ordered total on every rank
+__device__ __forceinline__ void peer_allreduce(const PeerParams& pr, double* payload, int* status)
+{
+    const int tid = threadIdx.x;
+    const int par = (int)(pr.epoch & 1ull);
+    const size_t my_box = ((size_t)par * pr.world + pr.rank) * pr.n;
+    for (int r = 0; r < pr.world; ++r) {
+        if (r == pr.rank) continue;
+        double* const dst = pr.mail[r] + my_box;
+        for (int i = tid; i < pr.n; i += blockDim.x) dst[i] = payload[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < pr.world && tid != pr.rank) {
+        st_release_sys_u64(pr.flag[tid] + ((size_t)par * pr.world + pr.rank) * 16, pr.epoch);
+        const unsigned long long* const mine = pr.flag[pr.rank] + ((size_t)par * pr.world + tid) * 16;
+        const unsigned long long t0 = global_timer_ns();
+        unsigned spins = 0;
+        while (ld_acquire_sys_u64(mine) < pr.epoch) {
+            if ((++spins & 255u) == 0 && (global_timer_ns() - t0 > kBarrierTimeoutNs || ld_volatile_i32(status) != 0)) {
+                atomicExch(status, 2);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    const double* const box = pr.mail[pr.rank] + (size_t)par * pr.world * pr.n;
+    for (int i = tid; i < pr.n; i += blockDim.x) {
+        const double own = payload[i];
+        double t = 0.0;
+        for (int r = 0; r < pr.world; ++r) t += (r == pr.rank) ? own : ld_relaxed_sys_f64(box + (size_t)r * pr.n + i);
+        payload[i] = t;
+    }
+    __syncthreads();
+}
+
+template <int CL, int CPL>
+__global__ void __launch_bounds__(kLikThreads, 1) logp_grad_sharded_kernel(const FusedParams f, const PeerParams pr)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    lik_stage_init(smem_raw);
+    __syncthreads();
+    uint32_t par = 0;
+    unsigned long long target = f.bar_base;
+    for (int cb = 0; cb < f.chain_blocks; ++cb) lik_phase<CL, CPL>(f.lik, smem_raw, blockIdx.x, cb, par);
+    grid_barrier(f.bar, target, f.status);
+    fin_phase(f.fin, smem_raw);            // finish_inline == 0: payload rows + local split genes
+    grid_barrier(f.bar, target, f.status);
+    if (blockIdx.x != 0) return;
+    peer_allreduce(pr, f.fin.payload, f.status);
+    // finish (what finish_kernel does after an NCCL all-reduce)
+    const FinParams& p = f.fin;
+    for (int ch = threadIdx.x; ch < p.Cp; ch += blockDim.x) {
+        const int Cp = p.Cp;
+        ChainSums s;
+        s.A_ll = p.payload[0 * Cp + ch];
+        s.A_e = p.payload[1 * Cp + ch];
+        s.S1 = p.payload[2 * Cp + ch];
+        s.S2 = p.payload[3 * Cp + ch];
+        finish_chain(p, ch, s, chain_const(p, ch));
+        if (p.first_gene_row >= 0)
+            finish_gene(p, 0, ch, p.payload[(size_t)(4 + p.first_gene_row) * Cp + ch], load_gene_coef(p, 0, ch, true));
+        if (p.last_gene_row >= 0 && !(p.G_local == 1 && p.first_gene_row >= 0))
+            finish_gene(p, p.G_local - 1, ch, p.payload[(size_t)(4 + p.last_gene_row) * Cp + ch],
+                        load_gene_coef(p, p.G_local - 1, ch, true));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // persistent NUTS tick kernel
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int& afl(const AsyncParams& p, int k, int c) { return p.afl[(size_t)k * p.n.Cp + c]; }
@@ -920,6 +1014,8 @@ static cudaError_t configure_fused_t()
     cudaError_t e = cudaFuncSetAttribute(logp_grad_fused_kernel<CL, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kLikSmemBytes);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(logp_grad_sharded_kernel<CL, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLikSmemBytes);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(nuts_tick_kernel<CL, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLikSmemBytes);
 }
 
@@ -942,6 +1038,13 @@ static cudaError_t launch_fused_t(const FusedParams& f, int n_cta, cudaStream_t 
                                        kLikSmemBytes, s);
 }
 template <int CL, int CPL>
+static cudaError_t launch_sharded_t(const FusedParams& f, const PeerParams& pr, int n_cta, cudaStream_t s)
+{
+    void* args[] = {const_cast<FusedParams*>(&f), const_cast<PeerParams*>(&pr)};
+    return cudaLaunchCooperativeKernel((const void*)logp_grad_sharded_kernel<CL, CPL>, dim3(n_cta), dim3(kLikThreads), args,
+                                       kLikSmemBytes, s);
+}
+template <int CL, int CPL>
 static cudaError_t launch_tick_t(const TickParams& t, int n_cta, cudaStream_t s)
 {
     void* args[] = {const_cast<TickParams*>(&t)};
@@ -956,6 +1059,16 @@ cudaError_t launch_logp_grad_fused(const FusedParams& f, int CL, int CPL, int n_
     if (CL == 16 && CPL == 1) return launch_fused_t<16, 1>(f, n_cta, s);
     if (CL == 32 && CPL == 1) return launch_fused_t<32, 1>(f, n_cta, s);
     if (CL == 32 && CPL == 2) return launch_fused_t<32, 2>(f, n_cta, s);
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_logp_grad_sharded(const FusedParams& f, const PeerParams& pr, int CL, int CPL, int n_cta, cudaStream_t s)
+{
+    if (CL == 4 && CPL == 1) return launch_sharded_t<4, 1>(f, pr, n_cta, s);
+    if (CL == 8 && CPL == 1) return launch_sharded_t<8, 1>(f, pr, n_cta, s);
+    if (CL == 16 && CPL == 1) return launch_sharded_t<16, 1>(f, pr, n_cta, s);
+    if (CL == 32 && CPL == 1) return launch_sharded_t<32, 1>(f, pr, n_cta, s);
+    if (CL == 32 && CPL == 2) return launch_sharded_t<32, 2>(f, pr, n_cta, s);
     return cudaErrorInvalidValue;
 }
 

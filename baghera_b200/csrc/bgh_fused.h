@@ -17,6 +17,16 @@ struct FusedParams {
     int chain_blocks;   // chain blocks of CL*CPL chains, walked sequentially by every CTA
 };
 
+// one-shot all-reduce of the payload over peer-mapped memory (NVLink P2P stores + system-scope flags)
+constexpr int kMaxPeers = 8;
+struct PeerParams {
+    double* mail[kMaxPeers];                  // mail[r]: rank r's mailbox [2 parities][world][n] (mail[rank] is local)
+    unsigned long long* flag[kMaxPeers];      // flag[r]: rank r's flags  [2 parities][world] x 16 words (128-byte lines)
+    int rank, world;
+    int n;                                    // payload doubles = payload rows * Cp
+    unsigned long long epoch;                 // launch counter, >= 1, identical on every rank
+};
+
 struct TickParams {
     FusedParams f;
     AsyncParams a;
@@ -29,6 +39,7 @@ struct TickParams {
 
 cudaError_t fused_configure();   // opt-in dynamic shared memory, once per process
 cudaError_t launch_logp_grad_fused(const FusedParams& f, int CL, int CPL, int n_cta, cudaStream_t s);
+cudaError_t launch_logp_grad_sharded(const FusedParams& f, const PeerParams& pr, int CL, int CPL, int n_cta, cudaStream_t s);
 cudaError_t launch_nuts_ticks(const TickParams& t, int CL, int CPL, int n_cta, cudaStream_t s);
 
 }  // namespace bgh

@@ -70,6 +70,7 @@ struct LikParams {
     int model;
     int fix;
     double c;
+    double gamma_rate;    // gamma model: rate of the Gamma prior (N_1kG), gene_regression.py:231
 };
 
 struct FinParams {
@@ -94,6 +95,7 @@ struct FinParams {
     int finish_inline;    // 1: single rank, write logp / grad rows 0..2 here
     double c;
     double lik_const;
+    double gamma_rate;
     // finish-only
     int first_gene_row, last_gene_row, G_local;
 };

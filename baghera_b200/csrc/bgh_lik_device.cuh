@@ -164,7 +164,9 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
     const int v = (cta * kLikWarps + warp) * SL + grp;
     const int Cp = p.Cp;
     const int ch0 = chain_block * CG + lc;   // chain of slot k is ch0 + k*CL
-    const bool gene_model = p.model == BGH_MODEL_GENE_NORMAL;
+    const bool gamma_model = p.model == BGH_MODEL_GENE_GAMMA;
+    const bool gene_model = p.model == BGH_MODEL_GENE_NORMAL || gamma_model;
+    const int row0 = gamma_model ? 2 : 3;   // first per-gene row of q / grad
 
     unsigned char* const warp_stage = smem_raw + (size_t)warp * kStages * kWarpStageBytes;
     const uint32_t bar0 = smem_u32(smem_raw + kLikStageBytes) + 8u * (uint32_t)((warp * kStages) * 8 + grp);   // stage s: + 64 s
@@ -177,7 +179,7 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
     const int ra = desc.x, rb = desc.y, flags = desc.z, g_first = desc.w;
     const bool exclusive = (flags & kExclusive) != 0;
     const bool active = ra < rb;
-    const double* const beta = p.q + (size_t)3 * Cp + ch0;   // gene model rows 3.. (this lane's chains)
+    const double* const beta = p.q + (size_t)row0 * Cp + ch0;   // per-gene rows (this lane's chains)
 
     const int base0 = ra & ~(CH - 1);   // CH aligned: every bulk copy source is 16-byte aligned
     const int n_chunks = active ? (rb - base0 + CH - 1) / CH : 0;
@@ -216,7 +218,14 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
         const int ch = ch0 + k * CL;
-        if (gene_model) {
+        if (gamma_model) {
+            // ref: gene_regression.py:229-248 — q = [e, mi_logodds__, beta_log__...]
+            const double ev = p.q[0 * Cp + ch];
+            const double xm = p.q[1 * Cp + ch];
+            iW2[k] = 0.0;
+            mi[k] = sigmoid_d(xm);
+            ne[k] = p.fix ? -1.0 : -ev;              // ref: gene_regression.py:234-240
+        } else if (gene_model) {
             const double xW = p.q[0 * Cp + ch];
             const double ev = p.q[1 * Cp + ch];
             const double xm = p.q[2 * Cp + ch];
@@ -244,11 +253,14 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
     double nb[CPL], db[CPL];   // nb = -c * beta
     double ag[CPL], ae[CPL], al[CPL], s1[CPL], s2[CPL], ax[CPL];
 #pragma unroll
+    // normal model: slope = c * beta_g,             db = beta_g - mi   (prior Normal(mi, W))
+    // gamma model : slope = c * exp(beta_log_g),    db = beta_log_g    (prior Gamma(mi, rate) on exp(.))
     for (int k = 0; k < CPL; ++k) {
-        nb[k] = -p.c * braw[k];
-        db[k] = braw[k] - mi[k];
+        nb[k] = -p.c * (gamma_model ? exp(braw[k]) : braw[k]);
+        db[k] = gamma_model ? braw[k] : braw[k] - mi[k];
         ag[k] = ae[k] = al[k] = s1[k] = s2[k] = ax[k] = 0.0;
     }
+    const double neg_inv_c = -1.0 / p.c;
 
     BGH_TRACE(1);
     if (active) {
@@ -280,8 +292,13 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
                     double* dst = p.slots + (size_t)(to_head ? v : p.NG + v) * Cp + ch0;
 #pragma unroll
                     for (int k = 0; k < CPL; ++k) dst[k * CL] = ag[k];
+                } else if (gamma_model) {
+                    // d/d beta_log = beta (c sum r - rate) + mi       (prior + log-Jacobian + likelihood)
+                    double* dst = p.grad + (size_t)(row0 + cur) * Cp + ch0;
+#pragma unroll
+                    for (int k = 0; k < CPL; ++k) dst[k * CL] = fma(nb[k] * neg_inv_c, fma(p.c, ag[k], -p.gamma_rate), mi[k]);
                 } else if (gene_model) {
-                    double* dst = p.grad + (size_t)(3 + cur) * Cp + ch0;
+                    double* dst = p.grad + (size_t)(row0 + cur) * Cp + ch0;
 #pragma unroll
                     for (int k = 0; k < CPL; ++k) dst[k * CL] = fma(p.c, ag[k], -db[k] * iW2[k]);
                 }
@@ -291,7 +308,7 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
 #pragma unroll
                 for (int k = 0; k < CPL; ++k) {
                     s1[k] += db[k];
-                    s2[k] = fma(db[k], db[k], s2[k]);
+                    s2[k] = gamma_model ? s2[k] + nb[k] * neg_inv_c : fma(db[k], db[k], s2[k]);   // sum beta / sum (beta-mi)^2
                 }
             }
         };
@@ -299,8 +316,8 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
         auto enter_gene = [&](int g, const double (&src)[CPL]) {
 #pragma unroll
             for (int k = 0; k < CPL; ++k) {
-                nb[k] = -p.c * src[k];
-                db[k] = src[k] - mi[k];
+                nb[k] = -p.c * (gamma_model ? exp(src[k]) : src[k]);
+                db[k] = gamma_model ? src[k] : src[k] - mi[k];
             }
             cur = g;
             load_beta(g + 1, bn);   // genes are consecutive after the sort
@@ -386,7 +403,7 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
                     }
 #pragma unroll
                     for (int k = 0; k < CPL; ++k) {
-                        nb2[k] = -p.c * raw2[k];
+                        nb2[k] = -p.c * (gamma_model ? exp(raw2[k]) : raw2[k]);
                         ag2[k] = 0.0;
                     }
 #pragma unroll

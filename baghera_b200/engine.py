@@ -11,7 +11,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import BGH_MODEL_GENE_NORMAL, BGH_MODEL_GW_NORMAL, BghError, bgh_cfg, check
+from ._lib import BGH_MODEL_GENE_GAMMA, BGH_MODEL_GENE_NORMAL, BGH_MODEL_GW_NORMAL, BghError, bgh_cfg, check
 
 
 def _ptr(t):
@@ -22,7 +22,9 @@ class Engine:
     """One context per GPU.  Parameters live on the device as float64[D, Cp] (gene-major, chain-minor)."""
 
     def __init__(self, chi2, ld, gene_id, n_genes, c, n_chains, model="gene", fix_intercept=False,
-                 device=0, shard=None):
+                 device=0, shard=None, gamma_rate=None):
+        """model: "gene" (normal prior, ref gene_regression.py:77-98), "gamma" (ref :229-248; pass
+        c = n_patients and gamma_rate = N_1kG) or "gw" (ref heritability.py:44-55)."""
         import torch
 
         if not torch.cuda.is_available():
@@ -34,10 +36,16 @@ class Engine:
         cfg = bgh_cfg()
         self.L.bgh_cfg_default(ctypes.byref(cfg))
         cfg.device = int(device)
-        cfg.model = BGH_MODEL_GENE_NORMAL if model == "gene" else BGH_MODEL_GW_NORMAL
+        if model not in ("gene", "gamma", "gw"):
+            raise ValueError("unknown model %r" % (model,))
+        cfg.model = {"gene": BGH_MODEL_GENE_NORMAL, "gamma": BGH_MODEL_GENE_GAMMA, "gw": BGH_MODEL_GW_NORMAL}[model]
+        if model == "gamma":
+            if gamma_rate is None:
+                raise ValueError("the gamma model needs gamma_rate (N_1kG)")
+            cfg.gamma_rate = float(gamma_rate)
         cfg.fix_intercept = int(bool(fix_intercept))
         cfg.n_snps = int(chi2.shape[0])
-        cfg.n_genes = int(n_genes) if model == "gene" else 1
+        cfg.n_genes = int(n_genes) if model != "gw" else 1
         cfg.n_chains = int(n_chains)
         cfg.c = float(c)
         if shard is not None:
@@ -50,7 +58,7 @@ class Engine:
         check(self.L.bgh_create(ctypes.byref(ctx), ctypes.byref(cfg)))
         self.ctx = ctx
         gid = None
-        if model == "gene":
+        if model != "gw":
             gid = np.ascontiguousarray(gene_id, dtype=np.int32)
             if gid.shape[0] != chi2.shape[0]:
                 raise ValueError("gene_id length mismatch")
@@ -115,6 +123,29 @@ class Engine:
     def logp_grad_finish(self, q_dc, payload, logp, grad):
         check(self.L.bgh_logp_grad_finish(self.ctx, _ptr(q_dc), _ptr(payload), _ptr(logp), _ptr(grad),
                                           self._stream()), self.ctx)
+
+    # ------------------------------------------------------------------ fused peer-memory exchange
+    def peer_export(self):
+        """Allocates this rank's mailbox; returns its CUDA IPC handle (bytes)."""
+        n = int(self.L.bgh_peer_handle_bytes())
+        buf = (ctypes.c_ubyte * n)()
+        check(self.L.bgh_peer_export(self.ctx, ctypes.cast(buf, ctypes.c_void_p)), self.ctx)
+        return bytes(buf)
+
+    def peer_connect(self, rank, world, handles):
+        """handles: list of `world` IPC handles (bytes) in rank order (all-gathered by the caller)."""
+        blob = b"".join(handles)
+        buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
+        check(self.L.bgh_peer_connect(self.ctx, int(rank), int(world), ctypes.cast(buf, ctypes.c_void_p)), self.ctx)
+
+    def logp_grad_sharded(self, q_dc, logp, grad):
+        """One launch per rank: local pass + one-shot all-reduce over peer memory + closing formulas."""
+        check(self.L.bgh_logp_grad_sharded(self.ctx, _ptr(q_dc), _ptr(logp), _ptr(grad), self._stream()), self.ctx)
+
+    def peer_status(self):
+        v = ctypes.c_int32()
+        check(self.L.bgh_peer_status(self.ctx, ctypes.byref(v)), self.ctx)
+        return v.value
 
     def logp_grad_host(self, q_cd, logp=None, grad=None, n_evals=None):
         """B1' with host buffers: q float64[C, D] (or [n, C, D]) numpy -> (logp, grad) numpy."""

@@ -134,7 +134,91 @@ def analyse_normal(snps_object, output_summary_filename, output_logger, SWEEPS, 
     return df
 
 
-def analyse_gamma(*args, **kwargs):
-    raise NotImplementedError(
-        "-m gamma (ref: gene_regression.py:183-325) is not on the B200 path yet: it shares the likelihood kernel "
-        "but needs the Gamma-prior closing kernel (SURVEY §8f rank 3). Use -m normal.")
+def analyse_gamma(snps_object, output_summary_filename, output_logger, SWEEPS, TUNE, CHAINS, CORES, N_1kG,
+                  fix_intercept=False):
+    """Bayesian hierarchical regression with the gamma model (ref: gene_regression.py:183-325).
+
+    ``e ~ Normal(1, 0.001)``, ``mi ~ Beta(1,1)``, ``beta ~ Gamma(alpha=mi, beta=N_1kG)``, likelihood mean
+    ``n_patients * beta[cat] * l + e`` (:229-247).  Free vector q = [e, mi_logodds__, beta_log__...].  The
+    likelihood kernel is the normal model's; only the prior / transform closing formulas differ.
+    Outputs as the reference: summary rows mi, herTOT, e (:274-280); per-gene columns from N_1kG * beta (:283),
+    P = mean(beta - mi / N_1kG > 0) (:232, :314)."""
+    import torch
+
+    from . import synth
+    from .engine import Engine
+    from .sampler import NutsSampler
+
+    snp_dataset = snps_object.table.copy().reset_index(drop=True)
+    n_patients = snps_object.n_patients
+    cat, Mg, genes = build_gene_index(snp_dataset)
+    G = len(genes)
+
+    logging.info("Model Evaluation Started")
+    logging.info("Average stats: %f" % np.mean(snps_object.table["stats"].values))
+
+    eng = Engine(snp_dataset["stats"].values.astype(np.float32), snp_dataset["l"].values.astype(np.float32),
+                 cat.astype(np.int32), G, float(n_patients), int(CHAINS), model="gamma", fix_intercept=bool(fix_intercept),
+                 device=OPTIONS["device"], gamma_rate=float(N_1kG))
+    sampler = NutsSampler(eng, seed=OPTIONS["seed"], target_accept=0.90)
+    start = synth.jittered_start(eng.D, int(CHAINS), seed=OPTIONS["seed"] + 1, model="gamma")
+    start[:, 2:] += np.log(1290028.0 / float(N_1kG))      # test value of Gamma(mi, N_1kG) = 0.5 / N_1kG
+    sampler.init(start)
+    dt = torch.float32 if OPTIONS["trace_dtype"] == "float32" else torch.float64
+    out = sampler.sample(int(SWEEPS), int(TUNE), trace_dtype=dt, progress=OPTIONS["progress"])
+    trace = out["trace"]                                           # [draws, D, C], unconstrained space
+    n_div = int(out["stats"][int(TUNE):, 3].sum())
+    if n_div:
+        logging.warning("There were %d divergences after tuning. Increase `target_accept` or reparameterize." % n_div)
+
+    te = trace[:, 0, :].double().cpu().numpy()
+    tmi_dev = torch.sigmoid(trace[:, 1, :].double())               # [draws, C]
+    tmi = tmi_dev.cpu().numpy()
+    w = torch.as_tensor(Mg.astype(np.float64), dtype=torch.float64, device=trace.device)
+    therTOT = np.zeros(te.shape)
+    chunk = 512
+    cols = {k: np.empty(G) for k in ("P", "bg_mean", "bg_median", "bg_var", "bg_5perc", "bg_95perc")}
+    draws, _, C = trace.shape
+    acc = torch.zeros((draws, C), dtype=torch.float64, device=trace.device)
+    for g0 in range(0, G, chunk):
+        g1 = min(G, g0 + chunk)
+        b = torch.exp(trace[:, 2 + g0:2 + g1, :].double())         # beta = exp(beta_log__)  [draws, g, C]
+        acc += torch.einsum("dgc,g->dc", b, w[g0:g1])              # herTOT = sum(beta * Mg)            (:233)
+        P = ((b - tmi_dev[:, None, :] / float(N_1kG)) > 0).double().mean(dim=(0, 2))     # diff (:232)
+        flat = (float(N_1kG) * b).permute(0, 2, 1).reshape(draws * C, g1 - g0)           # d["beta"] (:283)
+        q5, q50, q95 = device_quantiles(flat, (5.0, 50.0, 95.0))
+        cols["P"][g0:g1] = P.cpu().numpy()
+        cols["bg_mean"][g0:g1] = flat.mean(dim=0).cpu().numpy()
+        cols["bg_var"][g0:g1] = flat.var(dim=0, unbiased=False).cpu().numpy()
+        cols["bg_median"][g0:g1] = q50.cpu().numpy()
+        cols["bg_5perc"][g0:g1] = q5.cpu().numpy()
+        cols["bg_95perc"][g0:g1] = q95.cpu().numpy()
+    therTOT = acc.cpu().numpy()
+
+    if CHAINS > 1:
+        logging.info("evaluating Gelman-Rubin")
+        GR = {"mi": st.gelman_rubin(tmi)}
+        output_logger.info("DIAGNOSTIC (gelman-rubin) " + str(GR) + "\n"
+                           + "(If this number is >> 1 the method has some convergence problem, \n try increasing the number of s and b)")
+
+    logging.info("Writing output")
+    su = st.summary({"mi": tmi, "herTOT": therTOT, "e": te})                  # (:274-280)
+    su.to_csv(output_summary_filename, sep=",", mode="w")
+
+    output_logger.info(" Intercept: " + str(np.mean(te)) + " (sd= " + str(np.std(te)) + ")\n")
+    output_logger.info(" heritability from genes: " + str(np.median(therTOT)) + " (sd= " + str(np.std(therTOT)) + ")\n")
+    mi_mean, mi_median, mi_std = np.mean(tmi), np.median(tmi), np.std(tmi)
+    mi_5perc, mi_95perc = np.percentile(tmi, 5), np.percentile(tmi, 95)
+    output_logger.info(" Heritability: " + str(mi_mean) + " (std= " + str(mi_std) + ")\n" + "[ 5th perc= "
+                       + str(mi_5perc) + "," + " 95 perc= " + str(mi_95perc) + "]\n")
+
+    df = pd.DataFrame({"name": genes})
+    for k in ("P", "bg_mean", "bg_median", "bg_var", "bg_5perc", "bg_95perc"):
+        df[k] = cols[k]
+    df["mi_mean"] = mi_mean
+    df["mi_median"] = mi_median
+    analyse_gamma.last_run = dict(seconds_tune=out["seconds_tune"], seconds_draws=out["seconds_draws"],
+                                  leapfrogs=out["leapfrogs"], stats=out["stats"], kernel_launches=eng.launch_count)
+    eng.close()
+    logging.info("analysis done")
+    return df

@@ -62,3 +62,19 @@ def assemble_global_grad(shards_grads, shards, D):
         out[:, :3] = g[:, :3]
         out[:, 3 + sh.gene_lo: 3 + sh.gene_lo + sh.n_genes] = g[:, 3:]
     return out
+
+
+def connect_peers(engine, dist, device):
+    """One-off setup of the fused exchange: all-gather the ranks' mailbox IPC handles and map the peers.
+    `dist` is an initialised torch.distributed (NCCL or gloo) with one process per GPU of ONE node."""
+    import torch
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    h = engine.peer_export()
+    backend = dist.get_backend()
+    dev = device if backend == "nccl" else torch.device("cpu")
+    mine = torch.tensor(list(h), dtype=torch.uint8, device=dev)
+    allh = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine)
+    engine.peer_connect(rank, world, [bytes(t.cpu().tolist()) for t in allh])
+    dist.barrier()      # every mailbox is mapped (and zeroed) before anybody's first evaluation

@@ -182,6 +182,10 @@ def jittered_start(D: int, C: int, seed: int = 1, model: str = "gene") -> np.nda
         tp[0] = np.log(0.5)
         tp[1] = 1.0
         tp[2] = 0.0
+    elif model == "gamma":   # [e, mi_logodds__, beta_log__...]; Gamma(mi, N_1kG) test value = mean = 0.5 / N_1kG
+        tp = np.full(D, np.log(0.5 / N_1KG))
+        tp[0] = 1.0
+        tp[1] = 0.0
     else:  # gw: [e, mi_logodds__]; Beta(1,2) mean = 1/3
         tp = np.array([1.0, np.log((1 / 3) / (2 / 3))])
     return tp[None, :] + rng.uniform(-1.0, 1.0, size=(C, D))

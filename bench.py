@@ -115,14 +115,14 @@ def run_cpu_baseline(d, C, target_seconds=10.0, n_threads=0):
             "ms_per_chain_eval_per_core": dt / n * T * 1e3}
 
 
-def run_sampler_section(eng, args, C):
+def run_sampler_section(eng, args, C, seed=1):
     """ESS/s of the batched NUTS driver on the same dataset (secondary metric of BASELINE.json)."""
     import torch
     from baghera_b200 import stats as st
     from baghera_b200 import synth
     from baghera_b200.sampler import NutsSampler
-    smp = NutsSampler(eng, seed=1)
-    smp.init(synth.jittered_start(eng.D, C, seed=2))
+    smp = NutsSampler(eng, seed=seed)
+    smp.init(synth.jittered_start(eng.D, C, seed=1 + seed))
     l0 = eng.launch_count
     out = smp.sample(args.sampler_draws, args.sampler_tune, trace_dtype=torch.float32)
     tr = out["trace"]
@@ -218,6 +218,9 @@ def bench_gpu(args, wl):
         lc = torch.tensor([eng.lik_const], dtype=torch.float64, device=dev)
         dist.all_reduce(lc)
         eng.set_lik_const(float(lc.item()))
+        if args.exchange == "peer":
+            from baghera_b200.sharding import connect_peers
+            connect_peers(eng, dist, dev)
     Cp = eng.Cp
     logp = torch.empty(Cp, dtype=torch.float64, device=dev)
     grad = torch.zeros_like(q_dev)
@@ -227,6 +230,9 @@ def bench_gpu(args, wl):
     def step():
         if world == 1:
             eng.logp_grad(q_dev, logp, grad)
+        elif args.exchange == "peer":
+            # one launch per rank: local pass + one-shot all-reduce over NVLink peer memory + closing formulas
+            eng.logp_grad_sharded(q_dev, logp, grad)
         else:
             eng.logp_grad_local(q_dev, grad, payload)
             dist.all_reduce(payload)
@@ -292,16 +298,21 @@ def bench_gpu(args, wl):
         Ml, Dl = eng.M, eng.D
         b_alg = 12.0 * Ml + 16.0 * C * Dl + 8.0 * C           # SNP stream + read q + write grad + logp
         achieved = b_alg / (lik_ms * 1e-3) / 1e9 if lik_ms > 0 else 0.0
-        dp_instr = 6.0 * Ml * C
+        dp_instr = 5.0 * Ml * C                               # 5 DFMA per (SNP, chain): bgh_lik_device.cuh
         try:
             dfma_peak = eng.dfma_peak()
         except Exception:
             dfma_peak = None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
-                    "kernel": "lik_kernel", "kernel_ms": lik_ms, "finalize_ms": fin_ms,
+                    "kernel": "logp_grad_fused_kernel (likelihood pass | grid barrier | finalize, one launch)" if world == 1
+                    else "logp_grad_sharded_kernel (likelihood | finalize | peer all-reduce | finish, one launch)",
+                    "kernel_ms": lik_ms, "finalize_ms": fin_ms,
                     "algorithmic_bytes_per_launch": b_alg,
-                    "note": "at C=64 the kernel is FP64-pipe bound (6 DP instr per SNP x chain), see fp64_roofline"}
+                    "bytes_streamed_per_launch": 28.0 * Ml + 16.0 * C * Dl + 8.0 * C,
+                    "note": "algorithmic bytes per SURVEY 8d (fp32 chi2/ld + int32 gene id = 12 B/SNP); the kernel streams a prepared "
+                            "fp64 SoA (28 B/SNP) to keep conversions off the FP64 pipe. At C=64 the kernel is FP64-pipe bound "
+                            "(5 DFMA per SNP x chain), not HBM bound: see fp64_roofline for the binding roof"}
         fp64 = {"achieved_ginstr_s": dp_instr / (lik_ms * 1e-3) / 1e9 if lik_ms > 0 else 0.0,
                 "peak_ginstr_s": dfma_peak, "unit": "G FP64 lane-instr/s",
                 "frac": (dp_instr / (lik_ms * 1e-3) / 1e9 / dfma_peak) if (dfma_peak and lik_ms > 0) else None,
@@ -311,7 +322,8 @@ def bench_gpu(args, wl):
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["desc"], "M": M, "G": G, "chains": C,
-                       "parallelism": "single GPU" if world == 1 else "gene-block SNP sharding x%d + NCCL all-reduce of %d x %d fp64 payload" % (world, eng.payload_rows, Cp),
+                       "parallelism": "single GPU" if world == 1 else "gene-block SNP sharding x%d + %s of the %d x %d fp64 payload" % (
+                           world, "in-kernel one-shot all-reduce over NVLink peer memory" if args.exchange == "peer" else "NCCL all-reduce", eng.payload_rows, Cp),
                        "l2": "not flushed" if args.no_flush else "flushed between steps (256 MiB write, outside the per-step events)",
                        "timing": "per-step CUDA events on the launch stream, max over ranks"},
             "batched_evals_per_sec": 1e3 / step_ms,
@@ -343,6 +355,24 @@ def bench_gpu(args, wl):
         line["e2e"] = None
     if rank == 0 and world == 1 and not args.no_sampler:
         line["sampler"] = run_sampler_section(eng, args, C)
+    if world > 1 and not args.no_sampler:
+        # ESS/s at N GPUs: independent chain replicas (every rank runs its own C chains on the FULL dataset,
+        # no collective; the gene-block sharded tick kernel is not built yet)
+        eng.close()
+        eng = Engine(d.chi2, d.ld, d.gene_id, G, d.c, C, device=local_rank)
+        sm = run_sampler_section(eng, args, C, seed=1 + rank)
+        vec = torch.tensor([sm["ess_min_scalar"], sm["seconds_draws"], sm["ess_median_beta"],
+                            sm["chain_leapfrogs_per_sec_post_tune"]], dtype=torch.float64, device=dev)
+        allv = [torch.empty_like(vec) for _ in range(world)]
+        dist.all_gather(allv, vec)
+        if rank == 0:
+            A = torch.stack(allv).cpu().numpy()
+            secs = float(A[:, 1].max())
+            sm.update({"parallelism": "%d independent replicas x %d chains (one per GPU, different seeds)" % (world, C),
+                       "ess_min_scalar": float(A[:, 0].sum()), "ess_per_sec": float(A[:, 0].sum()) / secs,
+                       "ess_median_beta": float(A[:, 2].sum()), "ess_median_beta_per_sec": float(A[:, 2].sum()) / secs,
+                       "chain_leapfrogs_per_sec_post_tune": float(A[:, 3].sum()), "seconds_draws": secs})
+            line["sampler"] = sm
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = run_cpu_baseline(d, C, target_seconds=args.cpu_seconds)
     if rank == 0:
@@ -360,6 +390,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: payload all-reduce fused into the kernel over NVLink peer memory (default) or a separate NCCL call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-sampler", action="store_true", help="skip the ESS/s section")

@@ -49,7 +49,9 @@ enum {
 
 enum {
     BGH_MODEL_GENE_NORMAL = 0, /* gene_regression.py:77-98   */
-    BGH_MODEL_GW_NORMAL = 1    /* heritability.py:44-55      */
+    BGH_MODEL_GW_NORMAL = 1,   /* heritability.py:44-55      */
+    BGH_MODEL_GENE_GAMMA = 2   /* gene_regression.py:229-248: q = [e, mi_logodds__, beta_log___0..G-1], D = G + 2;
+                                  pass c = n_patients (the likelihood mean is n * beta * l + e) and gamma_rate = N_1kG */
 };
 
 typedef struct bgh_ctx bgh_ctx;
@@ -71,7 +73,9 @@ typedef struct bgh_cfg {
     int32_t last_gene_row;     /* payload row of the last gene if rank-shared, else -1 */
     int32_t n_shared_rows;     /* rank-shared genes over all ranks (payload rows 4 .. 4+n-1) */
     int32_t sm_count_override; /* 0 = query the device; tests may set it to build partitions on CPU */
-    int32_t reserved[5];
+    int32_t reserved0;
+    double  gamma_rate;        /* BGH_MODEL_GENE_GAMMA: rate of the Gamma(mi, rate) prior = N_1kG (gene_regression.py:231) */
+    int32_t reserved[2];
 } bgh_cfg;
 
 /* Fills *cfg with single-GPU defaults. */
@@ -115,6 +119,21 @@ int bgh_logp_grad(bgh_ctx* ctx, const double* q, double* logp, double* grad, voi
 int bgh_logp_grad_local(bgh_ctx* ctx, const double* q, double* grad, double* payload, void* stream);
 int bgh_logp_grad_finish(bgh_ctx* ctx, const double* q, const double* payload, double* logp,
                          double* grad, void* stream);
+
+/* Sharded form with the exchange fused into the kernel (one launch per rank and evaluation): after
+ * the local pass CTA 0 stores the payload into every peer's mailbox over NVLink (peer-mapped memory),
+ * raises a system-scope flag, waits for the peers and adds the contributions in rank order, then
+ * closes the formulas — no NCCL call on the hot path.  Setup (once): every rank calls
+ * bgh_peer_export (allocates its mailbox, returns a bgh_peer_handle_bytes()-byte CUDA IPC handle), the
+ * ranks all-gather the handles (torch.distributed) and call bgh_peer_connect(rank, world, handles);
+ * a barrier must separate the last connect from the first evaluation.  Every rank must call
+ * bgh_logp_grad_sharded the same number of times; one process per GPU, at most 8 ranks of one node.
+ * bgh_peer_status returns the device status word (0 ok, 1 grid barrier timeout, 2 peer timeout). */
+int32_t bgh_peer_handle_bytes(void);
+int bgh_peer_export(bgh_ctx* ctx, void* handle_out);
+int bgh_peer_connect(bgh_ctx* ctx, int32_t rank, int32_t world, const void* handles);
+int bgh_logp_grad_sharded(bgh_ctx* ctx, const double* q, double* logp, double* grad, void* stream);
+int bgh_peer_status(bgh_ctx* ctx, int32_t* status);
 
 /* B1' with HOST buffers in PyMC3's layout: q[C][D] -> logp[C], grad[C][D].  Copies H2D, transposes
  * on the device, evaluates, transposes back and copies D2H; synchronous.  Buffers may be pageable

@@ -264,3 +264,77 @@ def gw_fix_logp_grad_closed(q, chi2, ld, c):
     g[0] = float(np.sum(rw)) * (GW_FIX_HI - GW_FIX_LO) * sg * (1.0 - sg) + (1.0 - 2.0 * sg)
     g[1] = (c * float(np.sum(r)) - 1.0 / (1.0 - mi)) * mi * (1.0 - mi) + (1.0 - 2.0 * mi)
     return lp, g
+
+
+# --------------------------------------------------------------------------------------
+# Gamma model (ref: baghera_tool/gene_regression.py:229-248)
+#   e ~ Normal(1, sd=0.001); mi ~ Beta(1,1); beta ~ Gamma(alpha=mi, beta=N_1kG, shape=G)
+#   stats_j ~ Normal(n_patients * beta[cat_j] * l_j + e, sd=sqrt(l_j))
+# free vector (creation order :229-231): q = [e, mi_logodds__, beta_log___0 .. G-1], D = G + 2.
+# PyMC3 3.6 [recalled]: Gamma.logp = -gammaln(a) + a log(b) - b x + (a - 1) log(x); log transform jac = x.
+# --------------------------------------------------------------------------------------
+GAMMA_E_SD = 0.001
+
+
+def gamma_logp_pymc3_shaped(q, chi2, ld, cat, n_patients, rate, fix_intercept=False):
+    """(A) term-for-term, torch (autograd friendly)."""
+    import torch
+
+    e, mi_lo, blog = q[0], q[1], q[2:]
+    mi = torch.sigmoid(mi_lo)
+    beta = torch.exp(blog)
+    lp = q.new_zeros(())
+    tau = 1.0 / GAMMA_E_SD ** 2
+    lp = lp + (-tau * (e - 1.0) ** 2 + math.log(tau / math.pi / 2.0)) / 2.0                 # Normal(1, 0.001)   (:229)
+    a_, b_ = 1.0, 1.0
+    betaln = math.lgamma(a_) + math.lgamma(b_) - math.lgamma(a_ + b_)
+    lp = lp + ((a_ - 1.0) * torch.log(mi) + (b_ - 1.0) * torch.log1p(-mi) - betaln)          # Beta(1,1)          (:230)
+    lp = lp + torch.log(mi) + torch.log1p(-mi)                                                # logodds jacobian
+    lp = lp + torch.sum(-torch.lgamma(mi) + mi * math.log(rate) - rate * beta + (mi - 1.0) * torch.log(beta))   # (:231)
+    lp = lp + torch.sum(blog)                                                                 # log jacobian
+    chi2_t = torch.as_tensor(chi2, dtype=q.dtype)
+    ld_t = torch.as_tensor(ld, dtype=q.dtype)
+    cat_t = torch.as_tensor(cat, dtype=torch.long)
+    icpt = q.new_ones(()) if fix_intercept else e
+    mu = n_patients * beta[cat_t] * ld_t + icpt                                               # (:234-247)
+    tau_j = 1.0 / ld_t
+    lp = lp + torch.sum((-tau_j * (chi2_t - mu) ** 2 + torch.log(tau_j / math.pi / 2.0)) / 2.0)
+    return lp
+
+
+def gamma_logp_grad_autograd(q, chi2, ld, cat, n_patients, rate, fix_intercept=False):
+    import torch
+
+    qt = torch.tensor(np.asarray(q, dtype=np.float64), dtype=torch.float64, requires_grad=True)
+    lp = gamma_logp_pymc3_shaped(qt, chi2, ld, cat, n_patients, rate, fix_intercept)
+    (g,) = torch.autograd.grad(lp, qt)
+    return float(lp.detach()), g.numpy()
+
+
+def gamma_logp_grad_closed(q, chi2, ld, cat, n_patients, rate, fix_intercept=False):
+    """(B) hand-derived closed form (numpy + scipy.special)."""
+    from scipy.special import digamma, gammaln
+
+    q = np.asarray(q, dtype=np.float64)
+    G = q.shape[0] - 2
+    e, xm, x = q[0], q[1], q[2:]
+    mi = 1.0 / (1.0 + np.exp(-xm))
+    beta = np.exp(x)
+    icpt = 1.0 if fix_intercept else e
+    r = chi2 - icpt - n_patients * ld * beta[cat]
+    tau = 1.0 / GAMMA_E_SD ** 2
+    lp = -0.5 * tau * (e - 1.0) ** 2 + 0.5 * (math.log(tau) - LOG_2PI)
+    lp += math.log(mi) + math.log1p(-mi)
+    lp += G * (-gammaln(mi) + mi * math.log(rate)) - rate * beta.sum() + (mi - 1.0) * x.sum() + x.sum()
+    lp += -0.5 * np.sum(r * r / ld) + lik_const(ld)
+    g = np.empty_like(q)
+    g[0] = -tau * (e - 1.0) + (0.0 if fix_intercept else np.sum(r / ld))
+    g[1] = (1.0 - 2.0 * mi) + mi * (1.0 - mi) * (G * (math.log(rate) - digamma(mi)) + x.sum())
+    sums = np.bincount(cat, weights=r, minlength=G)
+    g[2:] = beta * (n_patients * sums - rate) + mi
+    return float(lp), g
+
+
+def gamma_batch_closed(Q, chi2, ld, cat, n_patients, rate, fix_intercept=False):
+    out = [gamma_logp_grad_closed(q, chi2, ld, cat, n_patients, rate, fix_intercept) for q in Q]
+    return np.array([o[0] for o in out]), np.stack([o[1] for o in out])

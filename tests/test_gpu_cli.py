@@ -71,9 +71,33 @@ def test_gw_heritability_end_to_end(snp_csv):
         assert needle in log, needle
 
 
-def test_gamma_model_is_declared_unsupported(snp_csv):
+def test_gene_heritability_gamma_end_to_end(snp_csv):
+    """-m gamma (ref: gene_regression.py:183-325): same artefacts; summary rows mi, herTOT, e; per-gene columns
+    from N_1kG * beta."""
     from baghera_b200.cli import main
     d, path, raw, truth = snp_csv
-    with pytest.raises(NotImplementedError, match="gamma"):
-        main(["gene-heritability", path, str(d / "g2.csv"), str(d / "s2.csv"), str(d / "l2.txt"), "-m", "gamma",
-              "--sweeps", "5", "-b", "5"])
+    out_g, out_s, out_l = str(d / "g2.csv"), str(d / "s2.csv"), str(d / "l2.txt")
+    rc = main(["gene-heritability", path, out_g, out_s, out_l, "-m", "gamma", "--sweeps", "400", "-b", "600",
+               "--n-chains", "4", "--seed", "5"])
+    assert rc == 0
+    res = pd.read_csv(out_g)
+    assert list(res.columns) == RESULT_COLUMNS
+    assert np.all(np.isfinite(res[["P", "bg_mean", "bg_median", "bg_var", "bg_5perc", "bg_95perc", "h2g"]].values))
+    assert (res["bg_mean"] > 0).all()                                      # beta ~ Gamma is positive
+    assert res["P"].between(0, 1).all()
+    su = pd.read_csv(out_s, index_col=0)
+    assert list(su.index) == ["mi", "herTOT", "e"] and list(su.columns) == SUMMARY_COLUMNS
+    assert abs(su.loc["e", "mean"] - 1.0) < 0.01                           # e ~ Normal(1, 0.001)
+    assert 0.0 < su.loc["mi", "mean"] < 1.0
+    # the enriched genes (largest simulated effects) still rank high
+    names = truth["names"]
+    kept = raw[raw["maf"] > 0.01]
+    counts = kept.groupby("gene").size()
+    expect = set(counts[counts >= 10].index) | {"NonCoding"}
+    hot = [names[i] for i in np.flatnonzero(truth["beta"] > truth["mi"] + 0.9) if names[i] in expect]
+    if hot:
+        r = res.set_index("name")
+        assert r.loc[hot, "bg_mean"].min() > r["bg_mean"].median()
+    log = open(out_l).read()
+    for needle in ("gene level regression, model: gamma", " Intercept: ", " heritability from genes: ", " Heritability: "):
+        assert needle in log, needle

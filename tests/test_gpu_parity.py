@@ -201,3 +201,26 @@ def test_full_size_properties():
     mid = 0.5 * (gs[0] + gs[2])
     assert np.max(np.abs(gs[1] - mid)) <= 1e-9 * np.max(np.abs(mid))
     eng.close()
+
+
+@pytest.mark.parametrize("C,fix", [(4, False), (64, False), (8, True)])
+def test_gamma_model(cfg1, C, fix):
+    """-m gamma (ref: gene_regression.py:229-248): q = [e, mi_logodds__, beta_log__...], slope n_patients * exp(beta_log)."""
+    import torch
+    from baghera_b200.engine import Engine
+    d = cfg1
+    eng = Engine(d.chi2, d.ld, d.gene_id, d.G, float(d.n_patients), C, model="gamma", fix_intercept=fix,
+                 gamma_rate=float(d.N_1kG))
+    assert eng.D == d.G + 2
+    Q = synth.jittered_start(d.G + 2, C, seed=40 + C, model="gamma")
+    Q[:, 0] = 1.0 + 1e-3 * np.random.default_rng(C).normal(size=C)      # e ~ N(1, 0.001)
+    logp, grad = eng.logp_grad(eng.to_device_layout(Q))
+    torch.cuda.synchronize()
+    lp = logp[:C].cpu().numpy()
+    g = eng.from_device_layout(grad).cpu().numpy()
+    lp_ref, g_ref = mo.gamma_batch_closed(Q, d.chi2.astype(np.float64), d.ld.astype(np.float64), d.gene_id.astype(np.int64),
+                                          float(d.n_patients), float(d.N_1kG), fix)
+    assert np.max(np.abs(lp - lp_ref) / np.abs(lp_ref)) <= REL_TOL
+    for i in range(C):
+        assert grad_rel_err(g[i], g_ref[i]) <= REL_TOL, "chain %d" % i
+    eng.close()

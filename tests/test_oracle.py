@@ -86,3 +86,28 @@ def test_synth_shapes():
     counts = np.bincount(d.gene_id, minlength=d.G)
     assert counts.min() >= 1 and counts[-1] == 9000 and d.gene_names[-1] == "NonCoding"
     assert abs(d.c - 361194 / 1290028) < 1e-15
+
+
+def test_gamma_model_forms_agree():
+    """Gamma model (ref: gene_regression.py:229-248): PyMC3-shaped autograd == closed form; finite differences."""
+    rng = np.random.default_rng(5)
+    M, G = 3000, 12
+    cat = rng.integers(0, G, M)
+    cat[:G] = np.arange(G)
+    ld = 1 + np.round(rng.lognormal(3.5, 1, M), 3)
+    n, rate = 361194.0, 1290028.0
+    beta = rng.gamma(0.3, 1 / rate, G) + 1e-9
+    chi2 = 1.02 + n * ld * beta[cat] + np.sqrt(ld) * rng.normal(size=M)
+    for fix in (False, True):
+        for trial in range(3):
+            q = np.concatenate([[1.0 + 1e-3 * rng.normal(), rng.normal()], np.log(beta) + rng.normal(0, 0.3, G)])
+            lp_a, g_a = mo.gamma_logp_grad_autograd(q, chi2, ld, cat, n, rate, fix)
+            lp_b, g_b = mo.gamma_logp_grad_closed(q, chi2, ld, cat, n, rate, fix)
+            assert abs(lp_a - lp_b) <= 1e-12 * abs(lp_a)
+            assert np.max(np.abs(g_a - g_b) / np.maximum(np.abs(g_a), 1e-9 * np.abs(g_a).max())) <= 1e-10
+    f = lambda v: mo.gamma_logp_grad_closed(v, chi2, ld, cat, n, rate)[0]
+    g_b = mo.gamma_logp_grad_closed(q, chi2, ld, cat, n, rate)[1]
+    for idx in (0, 1, 2, G + 1):
+        h = 1e-6 if idx != 0 else 1e-7
+        fd = (f(q + h * np.eye(G + 2)[idx]) - f(q - h * np.eye(G + 2)[idx])) / (2 * h)
+        assert abs(fd - g_b[idx]) <= 2e-5 * max(abs(g_b[idx]), 1.0), (idx, fd, g_b[idx])

@@ -1,0 +1,63 @@
+"""torchrun --nproc-per-node N tools/peer_check.py : sharded evaluation with the fused peer-memory exchange
+against (a) the NCCL path and (b) the oracle on rank 0; then timing of both exchanges."""
+import os, sys, time
+import numpy as np, torch
+import torch.distributed as dist
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from baghera_b200 import synth
+from baghera_b200.engine import Engine
+from baghera_b200.sharding import shard_dataset, connect_peers, assemble_global_grad
+
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dev = torch.device("cuda", lr)
+dist.init_process_group("nccl", device_id=dev)
+M, G, C = int(os.environ.get("M", 1_100_000)), int(os.environ.get("G", 15_000)), int(os.environ.get("C", 64))
+d = synth.make_arrays(M, G)
+Q = synth.jittered_start(G + 3, C, seed=1)
+sh = shard_dataset(d.chi2, d.ld, d.gene_id, G, rank, world)
+eng = Engine(sh.chi2, sh.ld, sh.gene_id, sh.n_genes, d.c, C, device=lr, shard=sh.cfg)
+lc = torch.tensor([eng.lik_const], dtype=torch.float64, device=dev)
+dist.all_reduce(lc)
+eng.set_lik_const(float(lc.item()))
+connect_peers(eng, dist, dev)
+q = eng.to_device_layout(sh.local_q(Q))
+Cp = eng.Cp
+lp1 = torch.empty(Cp, dtype=torch.float64, device=dev); g1 = torch.zeros_like(q)
+lp2 = torch.empty(Cp, dtype=torch.float64, device=dev); g2 = torch.zeros_like(q)
+payload = torch.zeros((eng.payload_rows, Cp), dtype=torch.float64, device=dev)
+
+def nccl_step():
+    eng.logp_grad_local(q, g1, payload)
+    dist.all_reduce(payload)
+    eng.logp_grad_finish(q, payload, lp1, g1)
+
+def fused_step():
+    eng.logp_grad_sharded(q, lp2, g2)
+
+nccl_step(); fused_step()
+torch.cuda.synchronize()
+assert eng.peer_status() == 0, eng.peer_status()
+a, b = lp1[:C].cpu().numpy(), lp2[:C].cpu().numpy()
+ga, gb = g1.cpu().numpy(), g2.cpu().numpy()
+err_lp = np.max(np.abs(a - b) / np.abs(a)); err_g = np.max(np.abs(ga - gb) / np.maximum(np.abs(ga), 1e-9 * np.abs(ga).max()))
+# every rank must hold bit-identical logp
+allp = [torch.empty_like(lp2) for _ in range(world)]
+dist.all_gather(allp, lp2)
+same = all(torch.equal(allp[0], t) for t in allp)
+for name, fn in (("nccl", nccl_step), ("fused", fused_step)):
+    for _ in range(20): fn()
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 500
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / n * 1e3], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0: print("%s exchange: %.2f us/step (max over %d ranks)" % (name, float(t), world), flush=True)
+assert eng.peer_status() == 0
+if rank == 0:
+    print("fused vs nccl: logp rel %.2e grad rel %.2e ; logp bit-identical on all ranks: %s" % (err_lp, err_g, same), flush=True)
+    assert err_lp < 1e-12 and err_g < 1e-9 and same
+eng.close()
+dist.destroy_process_group()
