@@ -642,7 +642,7 @@ static void fill_params(bgh_ctx* ctx, const double* q, double* grad, double* log
                         LikParams* lp, FinParams* fp)
 {
     lp->sp = ctx->d_xs; lp->wp = ctx->d_xw; lp->lp = ctx->d_xl; lp->gid = ctx->d_gid; lp->groups = ctx->d_groups;
-    lp->q = q; lp->grad = grad; lp->slots = ctx->d_slots; lp->part = ctx->d_part; lp->cc = ctx->d_cc; lp->trace = ctx->d_trace;
+    lp->q = q; lp->grad = grad; lp->ds = ctx->Cp; lp->cs = 1; fp->ds = ctx->Cp; fp->cs = 1; lp->slots = ctx->d_slots; lp->part = ctx->d_part; lp->cc = ctx->d_cc; lp->trace = ctx->d_trace;
     lp->Cp = ctx->Cp; lp->G = ctx->cfg.n_genes; lp->NG = ctx->n_groups; lp->n_cta = ctx->n_cta; lp->model = ctx->cfg.model;
     lp->fix = ctx->cfg.fix_intercept; lp->c = ctx->cfg.c; lp->gamma_rate = ctx->cfg.gamma_rate;
     fp->q = q; fp->grad = grad; fp->logp = logp; fp->slots = ctx->d_slots; fp->part = ctx->d_part; fp->cc = ctx->d_cc;
@@ -1103,22 +1103,34 @@ int bgh_nuts_run(bgh_ctx* ctx, const bgh_nuts_async_buffers* buf, const bgh_nuts
     double* const gw = buf->base.state + kSlotGW * vec;
     const int Dtot = cfg->n_dim_total > 0 ? cfg->n_dim_total : ctx->D;
     const double step0 = cfg->step_scale / pow((double)Dtot, 0.25);
+    if (ctx->cfg.n_chains > ctx->n_cta) return fail(ctx, BGH_EINVAL, "bgh_nuts_run: more chains than CTAs");
+    if (!ctx->fused) return fail(ctx, BGH_ESTATE, "bgh_nuts_run: needs the cooperative kernels (BGH_UNFUSED is set or the device cannot co-schedule the grid)");
     BGH_CUDA(ctx, nuts_async_launch_init(a, step0, 10.0, s));
-    // working position must be finite for every (also padded / finished) chain: start it at the current point
-    BGH_CUDA(ctx, cudaMemcpyAsync(qw, buf->base.state + kSlotQP * vec, sizeof(double) * vec, cudaMemcpyDeviceToDevice, s));
     ctx->launches += 1;
+    // Inside the run the sampler state is chain-major ([slot][Cp][D], see bgh_fused.cu): convert the slots
+    // the caller filled ([D][Cp]) — current point, its gradient, mass matrix and the adaptation windows —
+    // and give the working position a finite start (a copy of the current point) for every chain.
+    static const int kIoSlots[] = {kSlotQP, kSlotGP, kSlotVar, kSlotFgMean, kSlotFgRaw, kSlotBgMean, kSlotBgRaw};
+    double* const scratch = buf->base.state + kSlotPW * vec;
+    BGH_CUDA(ctx, cudaMemcpyAsync(qw, buf->base.state + kSlotQP * vec, sizeof(double) * vec, cudaMemcpyDeviceToDevice, s));   // [D][Cp]
+    for (int sl : kIoSlots) {
+        double* const x = buf->base.state + (size_t)sl * vec;
+        BGH_CUDA(ctx, launch_transpose_out(x, scratch, ctx->Cp, ctx->Cp, ctx->D, s));
+        BGH_CUDA(ctx, cudaMemcpyAsync(x, scratch, sizeof(double) * vec, cudaMemcpyDeviceToDevice, s));
+        ctx->launches += 1;
+    }
 
     // a transition needs at most 2^10 - 1 leaves; bound the loop so that a logic error cannot hang the GPU
     const int64_t max_ticks = (int64_t)(tune + draws) * 1024 + 1024;
     int64_t ticks = 0;
     int status = BGH_OK;
-    if (!ctx->fused) return fail(ctx, BGH_ESTATE, "bgh_nuts_run: needs the cooperative kernels (BGH_UNFUSED is set or the device cannot co-schedule the grid)");
     // persistent tick kernel (bgh_fused.cu): pre | likelihood | finalize | post | scalar per tick, grid
     // barriers in between; one cooperative launch runs up to `poll_ticks` ticks, then the host polls
     TickParams t;
     fill_params(ctx, qw, gw, buf->base.logp_w, ctx->d_payload, &t.f.lik, &t.f.fin);
     t.f.fin.finish_inline = 1;
     t.f.lik.trace = nullptr;
+    // (the working position / gradient exchanged with the likelihood pass stay gene-major [D][Cp])
     t.f.bar = ctx->d_bar; t.f.status = ctx->d_status; t.f.chain_blocks = ctx->chain_blocks;
     t.a = a;
     t.a.n.n_vec_blocks = ctx->n_cta;
@@ -1149,6 +1161,18 @@ int bgh_nuts_run(bgh_ctx* ctx, const bgh_nuts_async_buffers* buf, const bgh_nuts
         }
         *buf->base.n_active_host = ctx->h_poll[0];
         if (ctx->h_poll[0] >= ctx->cfg.n_chains) break;
+    }
+    // back to the caller's [D][Cp] layout
+    for (int sl : kIoSlots) {
+        double* const x = buf->base.state + (size_t)sl * vec;
+        cudaError_t e = launch_transpose_in(x, scratch, ctx->Cp, ctx->Cp, ctx->D, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(x, scratch, sizeof(double) * vec, cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess && status == BGH_OK) status = fail(ctx, BGH_ECUDA, std::string("bgh_nuts_run: ") + cudaGetErrorString(e));
+        ctx->launches += 1;
+    }
+    {
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess && status == BGH_OK) status = fail(ctx, BGH_ECUDA, std::string("bgh_nuts_run: ") + cudaGetErrorString(e));
     }
     if (status == BGH_OK && ticks >= max_ticks) status = fail(ctx, BGH_ESTATE, "bgh_nuts_run: tick budget exhausted");
     if (n_ticks) *n_ticks = ticks;

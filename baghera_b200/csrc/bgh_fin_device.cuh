@@ -49,7 +49,7 @@ __device__ __forceinline__ ChainConst chain_const(const FinParams& p, int ch)
         // ref: gene_regression.py:229-231.  e ~ Normal(1, 0.001); mi ~ Beta(1,1) (logodds);
         // beta_g ~ Gamma(alpha = mi, beta = rate) sampled as beta_log__:
         //   sum_g [ -lgamma(mi) + mi log(rate) - rate beta_g + (mi - 1) x_g + x_g ]   (x_g = log beta_g, Jacobian x_g)
-        const double e = p.q[0 * Cp + ch], xm = p.q[1 * Cp + ch];
+        const double e = p.q[0 * p.ds + ch * p.cs], xm = p.q[1 * p.ds + ch * p.cs];
         const double ax = fabs(xm);
         const double u = exp(-ax);
         const double L = log1p(u);
@@ -66,7 +66,7 @@ __device__ __forceinline__ ChainConst chain_const(const FinParams& p, int ch)
         return c;
     }
     if (p.model == BGH_MODEL_GENE_NORMAL) {
-        const double xW = p.q[0 * Cp + ch], e = p.q[1 * Cp + ch], xm = p.q[2 * Cp + ch];
+        const double xW = p.q[0 * p.ds + ch * p.cs], e = p.q[1 * p.ds + ch * p.cs], xm = p.q[2 * p.ds + ch * p.cs];
         const double ax = fabs(xm);
         const double u = exp(-ax);                 // one exp + one log1p serve sigmoid and both logs
         const double L = log1p(u);
@@ -82,7 +82,7 @@ __device__ __forceinline__ ChainConst chain_const(const FinParams& p, int ch)
         lp += p.lik_const;
         c.lp0 = lp;
     } else {
-        const double x0 = p.q[0 * Cp + ch], xm = p.q[1 * Cp + ch];
+        const double x0 = p.q[0 * p.ds + ch * p.cs], xm = p.q[1 * p.ds + ch * p.cs];
         const double ax = fabs(xm);
         const double u = exp(-ax);
         const double L = log1p(u);
@@ -111,27 +111,27 @@ __device__ __forceinline__ void finish_chain(const FinParams& p, int ch, const C
     const int Cp = p.Cp;
     if (p.model == BGH_MODEL_GENE_GAMMA) {
         // S1 = sum_g x_g, S2 = sum_g beta_g (owned genes)
-        const double e = p.q[0 * Cp + ch];
+        const double e = p.q[0 * p.ds + ch * p.cs];
         p.logp[ch] = c.lp0 + c.mi * s.S1 - p.gamma_rate * s.S2 - 0.5 * s.A_ll;
-        p.grad[0 * Cp + ch] = -kGammaETau * (e - 1.0) + (p.fix ? 0.0 : s.A_e);
-        p.grad[1 * Cp + ch] = 1.0 - 2.0 * c.mi + c.mi * (1.0 - c.mi) * (c.iW + s.S1);
+        p.grad[0 * p.ds + ch * p.cs] = -kGammaETau * (e - 1.0) + (p.fix ? 0.0 : s.A_e);
+        p.grad[1 * p.ds + ch * p.cs] = 1.0 - 2.0 * c.mi + c.mi * (1.0 - c.mi) * (c.iW + s.S1);
         return;
     }
     if (p.model == BGH_MODEL_GENE_NORMAL) {
-        const double e = p.q[1 * Cp + ch];
+        const double e = p.q[1 * p.ds + ch * p.cs];
         const double G = (double)p.G_total;
         p.logp[ch] = c.lp0 - 0.5 * s.S2 * c.iW2 - 0.5 * s.A_ll;
-        p.grad[0 * Cp + ch] = c.iW - 1.0 + s.S2 * c.iW2 - G;
-        p.grad[1 * Cp + ch] = -(e - 1.0) + (p.fix ? 0.0 : s.A_e);
-        p.grad[2 * Cp + ch] = 1.0 - 2.0 * c.mi + c.mi * (1.0 - c.mi) * s.S1 * c.iW2;
+        p.grad[0 * p.ds + ch * p.cs] = c.iW - 1.0 + s.S2 * c.iW2 - G;
+        p.grad[1 * p.ds + ch * p.cs] = -(e - 1.0) + (p.fix ? 0.0 : s.A_e);
+        p.grad[2 * p.ds + ch * p.cs] = 1.0 - 2.0 * c.mi + c.mi * (1.0 - c.mi) * s.S1 * c.iW2;
     } else {
-        const double x0 = p.q[0 * Cp + ch];
+        const double x0 = p.q[0 * p.ds + ch * p.cs];
         p.logp[ch] = c.lp0 - 0.5 * s.A_ll;
         if (p.fix) {
             const double sg = c.iW;
-            p.grad[0 * Cp + ch] = s.A_e * (kGwFixHi - kGwFixLo) * sg * (1.0 - sg) + (1.0 - 2.0 * sg);
+            p.grad[0 * p.ds + ch * p.cs] = s.A_e * (kGwFixHi - kGwFixLo) * sg * (1.0 - sg) + (1.0 - 2.0 * sg);
         } else {
-            p.grad[0 * Cp + ch] = -(x0 - 1.0) + s.A_e;
+            p.grad[0 * p.ds + ch * p.cs] = -(x0 - 1.0) + s.A_e;
         }
     }
 }
@@ -148,8 +148,8 @@ __device__ __forceinline__ GeneCoef load_gene_coef(const FinParams& p, int gene,
     if (needed) {
         gc.iW2 = p.cc[0 * p.Cp + ch];
         gc.mi = p.cc[1 * p.Cp + ch];
-        if (p.model == BGH_MODEL_GENE_NORMAL) gc.beta = p.q[(size_t)(3 + gene) * p.Cp + ch];
-        if (p.model == BGH_MODEL_GENE_GAMMA) gc.beta = exp(p.q[(size_t)(2 + gene) * p.Cp + ch]);
+        if (p.model == BGH_MODEL_GENE_NORMAL) gc.beta = p.q[(long long)(3 + gene) * p.ds + ch * p.cs];
+        if (p.model == BGH_MODEL_GENE_GAMMA) gc.beta = exp(p.q[(long long)(2 + gene) * p.ds + ch * p.cs]);
     }
     return gc;
 }
@@ -157,12 +157,12 @@ __device__ __forceinline__ void finish_gene(const FinParams& p, int gene, int ch
 {
     const int Cp = p.Cp;
     if (p.model == BGH_MODEL_GENE_GAMMA) {
-        p.grad[(size_t)(2 + gene) * Cp + ch] = fma(gc.beta, fma(p.c, sum_r, -p.gamma_rate), gc.mi);
+        p.grad[(long long)(2 + gene) * p.ds + ch * p.cs] = fma(gc.beta, fma(p.c, sum_r, -p.gamma_rate), gc.mi);
     } else if (p.model == BGH_MODEL_GENE_NORMAL) {
-        p.grad[(size_t)(3 + gene) * Cp + ch] = fma(p.c, sum_r, -(gc.beta - gc.mi) * gc.iW2);
+        p.grad[(long long)(3 + gene) * p.ds + ch * p.cs] = fma(p.c, sum_r, -(gc.beta - gc.mi) * gc.iW2);
     } else {
         // (c*sum_r - 1/(1-mi)) * mi(1-mi) + (1 - 2mi)
-        p.grad[1 * Cp + ch] = p.c * sum_r * gc.mi * (1.0 - gc.mi) + 1.0 - 3.0 * gc.mi;
+        p.grad[1 * p.ds + ch * p.cs] = p.c * sum_r * gc.mi * (1.0 - gc.mi) + 1.0 - 3.0 * gc.mi;
     }
 }
 

@@ -343,382 +343,390 @@ __device__ __forceinline__ void stamp(const PhaseTrace& pt, int k)
     if (pt.buf != nullptr && pt.row >= 0 && threadIdx.x == 0) pt.buf[(size_t)pt.row * 16 + k] = global_timer_ns();
 }
 
-struct TickIdx {
-    int chain, r0, rstep, tpr, rpb;
-    bool on;
+// ---------------------------------------------------------------------------------------------
+// Vector phases of the tick.  Inside bgh_nuts_run the sampler state is CHAIN-MAJOR ([slot][Cp][D], the
+// checkpoints [Cp][level][D] and the trace [draw][C][D]); only the two vectors exchanged with the
+// likelihood pass — working position QW and its gradient GW — stay gene-major [D][Cp].
+// Every CTA owns a contiguous block of rows (coordinates) of ALL chains, so all CTAs carry the same load
+// whatever the chains are doing.  Inside the CTA a warp works on one chain at a time (lane <-> row):
+// the chain's tree state is warp-uniform (no divergence, no predication) and every access to the ~20
+// per-chain vectors is a contiguous full-sector stream.  QW / GW pass through a shared-memory tile that
+// is loaded / stored with lane <-> chain (coalesced on the gene-major arrays) and read transposed.
+// Per-chain sums are reduced by a shuffle tree into partials[cta][quantity][chain]; the scalar phase adds
+// the CTAs in a fixed order.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTickMaxChains = 128;
+constexpr size_t kZSnapOffset = 0;                                   // int[kTickMaxChains]: chains that began a transition
+constexpr size_t kCmdOffset = 1024;                                   // per-phase copy of the chains' flags and scalars
+// shared-memory copy of afl[kAfCount][Cp] and sc[kAscCount][Cp] (one coalesced load per phase instead of
+// a dependent global load per chain and flag), followed by two tiles [rows][Cp + 1] of doubles
+struct ChainCmd {
+    const int* fl;       // [kAfCount][Cp]
+    const double* sc;    // [kAscCount][Cp]
+    int Cp;
+    __device__ __forceinline__ int f(int k, int c) const { return fl[k * Cp + c]; }
+    __device__ __forceinline__ double s(int k, int c) const { return sc[k * Cp + c]; }
 };
-__device__ __forceinline__ TickIdx tick_index(const NutsParams& p)
+__device__ __forceinline__ size_t tile_offset(int Cp)
 {
-    TickIdx v;
-    v.tpr = p.Cp < kLikThreads ? p.Cp : kLikThreads;   // threads along the chain axis (Cp <= kLikThreads)
-    v.rpb = kLikThreads / v.tpr;                       // rows per CTA pass
-    v.chain = threadIdx.x % v.tpr;
-    v.r0 = blockIdx.x * v.rpb + threadIdx.x / v.tpr;
-    v.rstep = gridDim.x * v.rpb;
-    v.on = v.chain < p.Cp && threadIdx.x < v.tpr * v.rpb;
+    return (kCmdOffset + (size_t)Cp * (kAfCount * sizeof(int) + kAscCount * sizeof(double)) + 127) & ~(size_t)127;
+}
+__device__ __forceinline__ ChainCmd load_cmd(const AsyncParams& a, unsigned char* smem_raw)
+{
+    const NutsParams& p = a.n;
+    double* const ssc = reinterpret_cast<double*>(smem_raw + kCmdOffset);
+    int* const sfl = reinterpret_cast<int*>(ssc + (size_t)kAscCount * p.Cp);
+    for (int i = threadIdx.x; i < kAscCount * p.Cp; i += kLikThreads) ssc[i] = p.sc[i];
+    for (int i = threadIdx.x; i < kAfCount * p.Cp; i += kLikThreads) sfl[i] = a.afl[i];
+    ChainCmd cm;
+    cm.fl = sfl; cm.sc = ssc; cm.Cp = p.Cp;
+    return cm;     // the caller synchronises the CTA before the first use
+}
+
+struct RowTile {
+    int r0, nr;            // rows [r0, r0 + nr) of this CTA in the current tile
+    int stride;            // Cp + 1 doubles (conflict-free transposed reads)
+    double* tq;            // working position tile
+    double* tg;            // gradient tile
+};
+__device__ __forceinline__ int tile_rows_max(int Cp)
+{
+    return (int)((kLikStageBytes - tile_offset(Cp)) / 2 / ((size_t)(Cp + 1) * sizeof(double)));
+}
+__device__ __forceinline__ double* slotc(const NutsParams& p, int s, int chain)
+{
+    return p.state + ((size_t)s * p.Cp + chain) * p.D;     // chain-major slot: [Cp][D]
+}
+// gene-major [D][Cp] -> tile (lane <-> chain: coalesced)
+__device__ __forceinline__ void tile_load(const NutsParams& p, const double* __restrict__ src, double* tile, const RowTile& T)
+{
+    const int Cp = p.Cp;
+    const int c = threadIdx.x % Cp, r = threadIdx.x / Cp, rstep = kLikThreads / Cp;
+    if (r < rstep)
+        for (int rr = r; rr < T.nr; rr += rstep) tile[rr * T.stride + c] = src[(size_t)(T.r0 + rr) * Cp + c];
+}
+__device__ __forceinline__ void tile_store(const NutsParams& p, double* __restrict__ dst, const double* tile, const RowTile& T)
+{
+    const int Cp = p.Cp;
+    const int c = threadIdx.x % Cp, r = threadIdx.x / Cp, rstep = kLikThreads / Cp;
+    if (r < rstep)
+        for (int rr = r; rr < T.nr; rr += rstep) dst[(size_t)(T.r0 + rr) * Cp + c] = tile[rr * T.stride + c];
+}
+// Accesses of the RARE per-chain vectors (tree edges, proposal, adaptation windows, Z, trace) carry an L2
+// evict-first policy so that they stream through without displacing the vectors every tick re-reads
+// (working position / momentum / gradient / mass matrix / running p_sum / low checkpoint levels).
+__device__ __forceinline__ double ldg_ef(const double* p, unsigned long long pol)
+{
+    double v;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stg_ef(double* p, double v, unsigned long long pol)
+{
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
 // ---- tick, vector part 1: pending end-of-doubling ops, trace record, mass-matrix adaptation, momentum
-// refresh of chains that start a transition, then the first half of the leapfrog for every running chain.
-// Two rows per iteration, every load of both rows issued before the first store (the phase is bound by
-// memory latency x serial iterations, not by bytes).
+// refresh of chains that start a transition, then the first half of the leapfrog for every running chain
 struct PreLoads {
-    double qw, pw, gw, var, qs, gs, pst, psr, qp, gp, fm, fr, bm, br, qe, pe, ge, z;
+    double pw, var, qs, gs, pst, psr, qp, gp, fm, fr, bm, br, qe, pe, ge, z;
 };
+
+__device__ __forceinline__ void pre_chain(const AsyncParams& a, const ChainCmd& cm, const RowTile& T, const int c, const int lane,
+                                          const bool first_tile)
+{
+    const NutsParams& p = a.n;
+    const int phase = cm.f(kAfPhase, c);
+    if (phase == kPhaseFinished) return;                           // warp-uniform
+    const bool merge = cm.f(kAfMerge, c) != 0, take = cm.f(kAfTake, c) != 0, take_top = cm.f(kAfTakeTop, c) != 0;
+    const bool is_new = cm.f(kAfNew, c) != 0, is_first = cm.f(kAfFirst, c) != 0;
+    const bool adapt = cm.f(kAfAdapt, c) != 0, sw = cm.f(kAfSwitch, c) != 0;
+    const int rec_slot = cm.f(kAfRecSlot, c);
+    const int dir = cm.f(kAfDir, c), dir_prev = cm.f(kAfDirPrev, c);
+    const double h = cm.s(kScH, c);
+    const bool flush = phase == kPhaseFlush;
+    // slot s of this chain lives at base + s * sstride (addresses are formed at the access)
+    double* const base = p.state + (size_t)c * p.D;
+    const size_t sstride = (size_t)p.Cp * p.D;
+#define SLOT(s) (base + (size_t)(s) * sstride)
+    double* const tq = T.tq + c;
+    const double* const tg = T.tg + c;
+    if (!merge && !is_new && !is_first && !flush) {
+        // ---- plain leaf inside a subtree (most chain-ticks): 2 global loads per row, 4 rows in flight
+        constexpr int U = 4;
+        for (int rr0 = lane; rr0 < T.nr; rr0 += 32 * U) {
+            double pw[U], var[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int rr = rr0 + 32 * u;
+                pw[u] = var[u] = 0.0;
+                if (rr < T.nr) { pw[u] = SLOT(kSlotPW)[T.r0 + rr]; var[u] = SLOT(kSlotVar)[T.r0 + rr]; }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int rr = rr0 + 32 * u;
+                if (rr < T.nr) {
+                    const int d = T.r0 + rr;
+                    const double q = tq[rr * T.stride], g = tg[rr * T.stride];
+                    if (take) { SLOT(kSlotQS)[d] = q; SLOT(kSlotGS)[d] = g; }
+                    const double ph = fma(h, g, pw[u]);
+                    SLOT(kSlotPW)[d] = ph;
+                    tq[rr * T.stride] = fma(2.0 * h * var[u], ph, q);
+                }
+            }
+        }
+        return;
+    }
+    // ---- general path (end of a doubling, start of a transition, flush)
+    const unsigned long long pol = l2_evict_first_policy();
+    double inv_fg = 0.0, inv_bg = 0.0;
+    if (is_new && adapt) { inv_fg = 1.0 / cm.s(kScFgUse, c); inv_bg = 1.0 / cm.s(kScBgUse, c); }
+    const bool ld_s = merge && take_top && !take;                 // proposal of the finished subtree
+    const bool ld_prop = (is_new || flush) && !(merge && take_top);
+    const bool ld_adapt = is_new && adapt && !flush;
+    const bool ld_z = is_new && !flush;
+    const bool ld_edge = !flush && !is_new && is_first && !(merge && dir == dir_prev);
+    const int eQ = dir > 0 ? kSlotQR : kSlotQL, eP = dir > 0 ? kSlotPR : kSlotPL, eG = dir > 0 ? kSlotGR : kSlotGL;
+    const bool rec = (is_new || flush) && rec_slot >= 0;
+    double kin0 = 0.0;
+    auto load = [&](int d, PreLoads& L) {
+        L.pw = SLOT(kSlotPW)[d]; L.var = SLOT(kSlotVar)[d];
+        L.qs = L.gs = L.pst = L.psr = L.qp = L.gp = L.fm = L.fr = L.bm = L.br = L.qe = L.pe = L.ge = L.z = 0.0;
+        if (ld_s) { L.qs = ldg_ef(SLOT(kSlotQS) + d, pol); L.gs = ldg_ef(SLOT(kSlotGS) + d, pol); }
+        if (merge) { L.pst = ldg_ef(SLOT(kSlotPSumTree) + d, pol); L.psr = SLOT(kSlotPSumRun)[d]; }
+        if (ld_prop) { L.qp = ldg_ef(SLOT(kSlotQP) + d, pol); L.gp = ldg_ef(SLOT(kSlotGP) + d, pol); }
+        if (ld_adapt) { L.fm = ldg_ef(SLOT(kSlotFgMean) + d, pol); L.fr = ldg_ef(SLOT(kSlotFgRaw) + d, pol); L.bm = ldg_ef(SLOT(kSlotBgMean) + d, pol); L.br = ldg_ef(SLOT(kSlotBgRaw) + d, pol); }
+        if (ld_z) L.z = ldg_ef(SLOT(kSlotZ) + d, pol);
+        if (ld_edge) { L.qe = ldg_ef(SLOT(eQ) + d, pol); L.pe = ldg_ef(SLOT(eP) + d, pol); L.ge = ldg_ef(SLOT(eG) + d, pol); }
+    };
+    auto process = [&](int rr, PreLoads& L) {
+        const int d = T.r0 + rr;
+        const double qw = tq[rr * T.stride], gw = tg[rr * T.stride];
+        double qp = L.qp, gp = L.gp;
+        if (merge) {     // the doubling that ended last tick was valid: fold it into the tree
+            const double qs = ld_s ? L.qs : qw, gs = ld_s ? L.gs : gw;
+            if (take) { stg_ef(SLOT(kSlotQS) + d, qw, pol); stg_ef(SLOT(kSlotGS) + d, gw, pol); }
+            if (take_top) { stg_ef(SLOT(kSlotQP) + d, qs, pol); stg_ef(SLOT(kSlotGP) + d, gs, pol); qp = qs; gp = gs; }
+            if (dir_prev > 0) { stg_ef(SLOT(kSlotQR) + d, qw, pol); stg_ef(SLOT(kSlotPR) + d, L.pw, pol); stg_ef(SLOT(kSlotGR) + d, gw, pol); }
+            else { stg_ef(SLOT(kSlotQL) + d, qw, pol); stg_ef(SLOT(kSlotPL) + d, L.pw, pol); stg_ef(SLOT(kSlotGL) + d, gw, pol); }
+            stg_ef(SLOT(kSlotPSumTree) + d, L.pst + L.psr, pol);
+        }
+        if (rec) {
+            const size_t t = ((size_t)rec_slot * p.C + c) * p.D + d;          // trace [draw][C][D]
+            if (a.trace_f32) reinterpret_cast<float*>(a.trace)[t] = (float)qp;
+            else reinterpret_cast<double*>(a.trace)[t] = qp;
+        }
+        if (flush) return;
+        double q, mom, g, var = L.var;
+        if (is_new) {
+            if (adapt) {   // quadpotential.QuadPotentialDiagAdapt.update with the sample just produced
+                double fm = L.fm, fr = L.fr, bm = L.bm, br = L.br;
+                welford_add(qp, inv_fg, fm, fr);
+                welford_add(qp, inv_bg, bm, br);
+                var = fr * inv_fg;
+                SLOT(kSlotVar)[d] = var;
+                if (sw) { stg_ef(SLOT(kSlotFgMean) + d, bm, pol); stg_ef(SLOT(kSlotFgRaw) + d, br, pol); stg_ef(SLOT(kSlotBgMean) + d, 0.0, pol); stg_ef(SLOT(kSlotBgRaw) + d, 0.0, pol); }
+                else { stg_ef(SLOT(kSlotFgMean) + d, fm, pol); stg_ef(SLOT(kSlotFgRaw) + d, fr, pol); stg_ef(SLOT(kSlotBgMean) + d, bm, pol); stg_ef(SLOT(kSlotBgRaw) + d, br, pol); }
+            }
+            mom = L.z * rsqrt(var);          // p ~ N(0, 1/var); z was drawn ahead of time (slot Z)
+            stg_ef(SLOT(kSlotPL) + d, mom, pol); stg_ef(SLOT(kSlotPR) + d, mom, pol); stg_ef(SLOT(kSlotPSumTree) + d, mom, pol);
+            stg_ef(SLOT(kSlotQL) + d, qp, pol); stg_ef(SLOT(kSlotQR) + d, qp, pol); stg_ef(SLOT(kSlotGL) + d, gp, pol); stg_ef(SLOT(kSlotGR) + d, gp, pol);
+            kin0 = fma(0.5 * var * mom, mom, kin0);
+            q = qp; g = gp;
+        } else if (is_first) {
+            if (merge && dir == dir_prev) { q = qw; mom = L.pw; g = gw; }
+            else { q = L.qe; mom = L.pe; g = L.ge; }
+        } else {
+            q = qw; mom = L.pw; g = gw;
+            if (take) { stg_ef(SLOT(kSlotQS) + d, q, pol); stg_ef(SLOT(kSlotGS) + d, g, pol); }
+        }
+        const double ph = fma(h, g, mom);
+        SLOT(kSlotPW)[d] = ph;
+        tq[rr * T.stride] = fma(2.0 * h * var, ph, q);
+    };
+    for (int rr0 = lane; rr0 < T.nr; rr0 += 64) {
+        PreLoads L0, L1;
+        const bool two = rr0 + 32 < T.nr;
+        load(T.r0 + rr0, L0);
+        if (two) load(T.r0 + rr0 + 32, L1);
+        process(rr0, L0);
+        if (two) process(rr0 + 32, L1);
+    }
+#undef SLOT
+    if (is_new && !flush) {     // kinetic energy of the fresh momenta -> quantity kAqKin0 (added over the tiles)
+        const double t = warp_sum(kin0);
+        if (lane == 0) {
+            double* const dst = p.partials + ((size_t)blockIdx.x * kAsyncPartials + kAqKin0) * p.Cp + c;
+            *dst = (first_tile ? 0.0 : *dst) + t;
+        }
+    }
+}
 
 __device__ __forceinline__ void tick_pre(const AsyncParams& a, unsigned char* smem_raw, const PhaseTrace& pt)
 {
     const NutsParams& p = a.n;
-    const TickIdx v = tick_index(p);
-    double kin0 = 0.0;
-    const int c = v.chain;
-    const int phase = v.on ? afl(a, kAfPhase, c) : kPhaseFinished;
-    if (phase != kPhaseFinished) {
-        const bool merge = afl(a, kAfMerge, c) != 0, take = afl(a, kAfTake, c) != 0, take_top = afl(a, kAfTakeTop, c) != 0;
-        const bool is_new = afl(a, kAfNew, c) != 0, is_first = afl(a, kAfFirst, c) != 0;
-        const bool adapt = afl(a, kAfAdapt, c) != 0, sw = afl(a, kAfSwitch, c) != 0;
-        const int rec_slot = afl(a, kAfRecSlot, c);
-        const int dir = afl(a, kAfDir, c), dir_prev = afl(a, kAfDirPrev, c);
-        const double h = sc(p, kScH, c);
-        double inv_fg = 0.0, inv_bg = 0.0;
-        if (is_new && adapt) { inv_fg = 1.0 / sc(p, kScFgUse, c); inv_bg = 1.0 / sc(p, kScBgUse, c); }
-        double* const VAR = slot(p, kSlotVar);
-        double* const QW = slot(p, kSlotQW);
-        double* const PW = slot(p, kSlotPW);
-        double* const GW = slot(p, kSlotGW);
-        double* const QS = slot(p, kSlotQS);
-        double* const GS = slot(p, kSlotGS);
-        double* const QP = slot(p, kSlotQP);
-        double* const GP = slot(p, kSlotGP);
-        double* const PST = slot(p, kSlotPSumTree);
-        const double* const PSR = slot(p, kSlotPSumRun);
-        double* const QL = slot(p, kSlotQL);
-        double* const PL = slot(p, kSlotPL);
-        double* const GL = slot(p, kSlotGL);
-        double* const QR = slot(p, kSlotQR);
-        double* const PR = slot(p, kSlotPR);
-        double* const GR = slot(p, kSlotGR);
-        double* const FM = slot(p, kSlotFgMean);
-        double* const FR = slot(p, kSlotFgRaw);
-        double* const BM = slot(p, kSlotBgMean);
-        double* const BR = slot(p, kSlotBgRaw);
-        const double* const Z = slot(p, kSlotZ);
-        // per-chain, loop-invariant load predicates
-        const bool flush = phase == kPhaseFlush;
-        const bool ld_s = merge && take_top && !take;                 // proposal of the finished subtree
-        const bool ld_prop = (is_new || flush) && !(merge && take_top);
-        const bool ld_adapt = is_new && adapt && !flush;
-        const bool ld_z = is_new && !flush;
-        const bool ld_edge = !flush && !is_new && is_first && !(merge && dir == dir_prev);
-        const double* const QE = dir > 0 ? QR : QL;
-        const double* const PE = dir > 0 ? PR : PL;
-        const double* const GE = dir > 0 ? GR : GL;
-
-        auto load = [&](int d, PreLoads& L) {
-            const size_t i = (size_t)d * p.Cp + c;
-            L.qw = QW[i]; L.pw = PW[i]; L.gw = GW[i]; L.var = VAR[i];
-            L.qs = L.qw; L.gs = L.gw;
-            L.pst = L.psr = L.qp = L.gp = L.fm = L.fr = L.bm = L.br = L.qe = L.pe = L.ge = L.z = 0.0;
-            if (ld_s) { L.qs = QS[i]; L.gs = GS[i]; }
-            if (merge) { L.pst = PST[i]; L.psr = PSR[i]; }
-            if (ld_prop) { L.qp = QP[i]; L.gp = GP[i]; }
-            if (ld_adapt) { L.fm = FM[i]; L.fr = FR[i]; L.bm = BM[i]; L.br = BR[i]; }
-            if (ld_z) L.z = Z[i];
-            if (ld_edge) { L.qe = QE[i]; L.pe = PE[i]; L.ge = GE[i]; }
-        };
-        auto process = [&](int d, PreLoads& L) {
-            const size_t i = (size_t)d * p.Cp + c;
-            double qp = L.qp, gp = L.gp;
-            // ---- the doubling that ended last tick was valid: fold it into the tree
-            if (merge) {
-                if (take) { QS[i] = L.qw; GS[i] = L.gw; }
-                if (take_top) { QP[i] = L.qs; GP[i] = L.gs; qp = L.qs; gp = L.gs; }
-                if (dir_prev > 0) { QR[i] = L.qw; PR[i] = L.pw; GR[i] = L.gw; }
-                else { QL[i] = L.qw; PL[i] = L.pw; GL[i] = L.gw; }
-                PST[i] = L.pst + L.psr;
-            }
-            if ((is_new || flush) && rec_slot >= 0 && c < p.C) {
-                const size_t t = ((size_t)rec_slot * p.D + d) * p.C + c;
-                if (a.trace_f32) reinterpret_cast<float*>(a.trace)[t] = (float)qp;
-                else reinterpret_cast<double*>(a.trace)[t] = qp;
-            }
-            if (flush) return;
-            double q, mom, g, var = L.var;
-            if (is_new) {
-                if (adapt) {   // quadpotential.QuadPotentialDiagAdapt.update with the sample just produced
-                    double fm = L.fm, fr = L.fr, bm = L.bm, br = L.br;
-                    welford_add(qp, inv_fg, fm, fr);
-                    welford_add(qp, inv_bg, bm, br);
-                    var = fr * inv_fg;
-                    VAR[i] = var;
-                    if (sw) { FM[i] = bm; FR[i] = br; BM[i] = 0.0; BR[i] = 0.0; }
-                    else { FM[i] = fm; FR[i] = fr; BM[i] = bm; BR[i] = br; }
-                }
-                mom = L.z * rsqrt(var);          // p ~ N(0, 1/var); z was drawn ahead of time (slot Z)
-                PL[i] = mom; PR[i] = mom; PST[i] = mom;
-                QL[i] = qp; QR[i] = qp; GL[i] = gp; GR[i] = gp;
-                kin0 = fma(0.5 * var * mom, mom, kin0);
-                q = qp; g = gp;
-            } else if (is_first) {
-                if (merge && dir == dir_prev) { q = L.qw; mom = L.pw; g = L.gw; }
-                else { q = L.qe; mom = L.pe; g = L.ge; }
-            } else {
-                q = L.qw; mom = L.pw; g = L.gw;
-                if (take) { QS[i] = q; GS[i] = g; }
-            }
-            const double ph = fma(h, g, mom);
-            PW[i] = ph;
-            QW[i] = fma(2.0 * h * var, ph, q);
-        };
-        int d = v.r0;
-        for (; d + v.rstep < p.D; d += 2 * v.rstep) {
-            PreLoads L0, L1;
-            load(d, L0);
-            load(d + v.rstep, L1);
-            process(d, L0);
-            process(d + v.rstep, L1);
-        }
-        if (d < p.D) {
-            PreLoads L0;
-            load(d, L0);
-            process(d, L0);
-        }
-    }
-    // kinetic energy of the fresh momenta -> quantity kAqKin0 (fixed-order CTA reduction)
-    {
-        double* const red = reinterpret_cast<double*>(smem_raw);
-        red[threadIdx.x] = kin0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rpc = (p.D + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int r_begin = (int)blockIdx.x * rpc, r_end = min(p.D, r_begin + rpc);
+    const int trmax = tile_rows_max(p.Cp);
+    const int n_tiles = (rpc + trmax - 1) / trmax, tr = (rpc + n_tiles - 1) / n_tiles;
+    RowTile T;
+    T.stride = p.Cp + 1;
+    T.tq = reinterpret_cast<double*>(smem_raw + tile_offset(p.Cp));
+    T.tg = T.tq + (size_t)tr * T.stride;
+    const double* const GWg = slot(p, kSlotGW);     // gene-major [D][Cp]
+    double* const QWg = slot(p, kSlotQW);
+    const ChainCmd cm = load_cmd(a, smem_raw);
+    for (int t0 = r_begin; t0 < r_end; t0 += tr) {
+        T.r0 = t0;
+        T.nr = min(tr, r_end - t0);
+        tile_load(p, QWg, T.tq, T);
+        tile_load(p, GWg, T.tg, T);
         __syncthreads();
-        if (threadIdx.x < v.tpr && v.on) {
-            double t = 0.0;
-            for (int r = 0; r < v.rpb; ++r) t += red[r * v.tpr + threadIdx.x];
-            p.partials[((size_t)blockIdx.x * kAsyncPartials + kAqKin0) * p.Cp + c] = t;
-        }
+        for (int c = warp; c < p.C; c += kLikWarps) pre_chain(a, cm, T, c, lane, t0 == r_begin);
+        __syncthreads();
+        tile_store(p, QWg, T.tq, T);
         __syncthreads();
     }
 }
 
-// ---- tick, vector part 2: second half kick + per-chain reductions (kinetic, sub-block U-turn dots for
-// the chain's own checkpoint levels, speculative whole-tree dots on the last leaf of a doubling).
-//
-// Every CTA owns a contiguous block of rows and walks it in tiles of 32 rows x all chains:
-//   core pass   lane <-> chain (the [D][Cp] state arrays are chain-minor: coalesced): half kick, running
-//               p_sum, kinetic and whole-tree dots; {p, p_sum, var} of the tile go to shared memory
-//   level pass  lane <-> row, warp <-> chain (transposed through shared memory): the checkpoints are
-//               chain-major [Cp][level][D], so the store of the chain's new checkpoint (even leaves) and
-//               the loads of the levels it checks (odd leaves) are contiguous 512-byte warp accesses no
-//               matter which level each chain is at; the per-(chain, level) dots are reduced by a
-//               shuffle tree and accumulated in shared memory, tile after tile (fixed order).
-constexpr int kTileRows = 32;
-constexpr int kTickMaxChains = 128;   // shared-memory budget of the post phase
-struct PostLayout {
-    int stride;            // tile row stride in doubles (tpr + 1: conflict-free transposed reads)
-    double* t_mom;         // [kTileRows][stride]
-    double* t_ps;
-    double* t_var;
-    double* l_acc;         // [tpr][2 * kNutsMaxDepth]
-    int4* cmd;             // [tpr] {n_lvl, lvl_min, store_level, running}
-    double* red;           // [3][kLikThreads] (reuses the tile area after the last tile)
-};
-__device__ __forceinline__ PostLayout post_layout(unsigned char* smem_raw, int tpr)
+// second half kick + reductions for the rows of the tile of one chain that checks NL checkpoint levels
+// (kinetic, NL pairs of sub-block U-turn dots, whole-tree dots on the last leaf of a doubling);
+// U rows per lane and iteration with all loads first.  Everything but the row index is warp-uniform.
+template <int NL, int U>
+__device__ __forceinline__ void post_rows(const NutsParams& p, const RowTile& T, const int c, const int lane, const int leaf,
+                                          const int store_level, const int lvl_min, const bool last, const int dir,
+                                          const double h, const bool first_tile)
 {
-    PostLayout L;
-    L.stride = tpr + 1;
-    double* base = reinterpret_cast<double*>(smem_raw);
-    L.t_mom = base;
-    L.t_ps = L.t_mom + kTileRows * L.stride;
-    L.t_var = L.t_ps + kTileRows * L.stride;
-    L.l_acc = base + (size_t)3 * kTileRows * (kTickMaxChains + 1);          // fixed offsets: the tile area is
-    L.cmd = reinterpret_cast<int4*>(L.l_acc + (size_t)kTickMaxChains * 2 * kNutsMaxDepth);   // sized for kTickMaxChains
-    L.red = base;
-    return L;
+    const double* const VAR = slotc(p, kSlotVar, c);
+    double* const PW = slotc(p, kSlotPW, c);
+    double* const PSR = slotc(p, kSlotPSumRun, c);
+    const double* const PST = slotc(p, kSlotPSumTree, c);
+    const double* const PO = slotc(p, dir > 0 ? kSlotPL : kSlotPR, c);
+    const double* const tg = T.tg + c;
+    double a_kin = 0.0, a_t0 = 0.0, a_t1 = 0.0;
+    double lv[2 * (NL > 0 ? NL : 1)];
+#pragma unroll
+    for (int k = 0; k < 2 * (NL > 0 ? NL : 1); ++k) lv[k] = 0.0;
+    for (int rr0 = lane; rr0 < T.nr; rr0 += 32 * U) {
+        double var[U], pwv[U], psr[U], pstv[U], pov[U];
+        double2 ck[U][NL > 0 ? NL : 1];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int rr = rr0 + 32 * u, d = T.r0 + rr;
+            var[u] = pwv[u] = psr[u] = pstv[u] = pov[u] = 0.0;
+#pragma unroll
+            for (int l = 0; l < NL; ++l) ck[u][l] = make_double2(0.0, 0.0);
+            if (rr < T.nr) {
+                var[u] = VAR[d]; pwv[u] = PW[d];
+                if (leaf != 0) psr[u] = PSR[d];
+                if (last) { pstv[u] = PST[d]; pov[u] = PO[d]; }
+#pragma unroll
+                for (int l = 0; l < NL; ++l) ck[u][l] = *ckpt2(p, lvl_min + l, d, c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int rr = rr0 + 32 * u, d = T.r0 + rr;
+            if (rr < T.nr) {
+                const double mom = fma(h, tg[rr * T.stride], pwv[u]);
+                PW[d] = mom;
+                const double vel = var[u] * mom;
+                a_kin = fma(0.5 * vel, mom, a_kin);
+                const double ps = psr[u] + mom;
+                PSR[d] = ps;
+                if (store_level >= 0) *ckpt2(p, store_level, d, c) = make_double2(mom, ps);
+#pragma unroll
+                for (int l = 0; l < NL; ++l) {
+                    const double pc = ck[u][l].x;
+                    const double sub = ps - ck[u][l].y + pc;
+                    lv[2 * l] = fma(sub, var[u] * pc, lv[2 * l]);
+                    lv[2 * l + 1] = fma(sub, vel, lv[2 * l + 1]);
+                }
+                if (last) {
+                    const double pst = pstv[u] + ps;
+                    a_t0 = fma(pst, vel, a_t0);
+                    a_t1 = fma(pst, var[u] * pov[u], a_t1);
+                }
+            }
+        }
+    }
+    // warp sums -> partials[cta][quantity][chain] (accumulated over the tiles of this CTA, in order)
+    double* const out = p.partials + (size_t)blockIdx.x * kAsyncPartials * p.Cp + c;
+    auto emit = [&](int k, double v) {
+        const double t = warp_sum(v);
+        if (lane == 0) out[(size_t)k * p.Cp] = (first_tile ? 0.0 : out[(size_t)k * p.Cp]) + t;
+    };
+    emit(0, a_kin);
+#pragma unroll
+    for (int k = 0; k < 2 * NL; ++k) emit(1 + k, lv[k]);
+    if (last) {
+        emit(kAqTree0, a_t0);
+        emit(kAqTree0 + 1, a_t1);
+    }
 }
-constexpr size_t kPostSmemBytes = ((size_t)3 * kTileRows * (kTickMaxChains + 1) + (size_t)kTickMaxChains * 2 * kNutsMaxDepth) * sizeof(double) +
-                                  (size_t)kTickMaxChains * sizeof(int4);
-constexpr size_t kZSnapOffset = kPostSmemBytes;   // snapshot of the chains that began a transition (Z refill)
-static_assert(kZSnapOffset + kTickMaxChains * sizeof(int) <= kLikStageBytes, "post-phase shared memory");
-static_assert((size_t)3 * kLikThreads * sizeof(double) <= (size_t)3 * kTileRows * (kTickMaxChains + 1) * sizeof(double), "reduction area inside the tile area");
 
+// ---- tick, vector part 2: second half kick + per-chain reductions
 __device__ __forceinline__ void tick_post(const AsyncParams& a, unsigned char* smem_raw, const PhaseTrace& pt)
 {
     const NutsParams& p = a.n;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tpr = p.Cp;                       // threads along the chain axis (Cp <= kTickMaxChains)
-    const int rpb = kLikThreads / tpr;          // rows per CTA pass of the core mapping
-    const int c = tid % tpr, rs = tid / tpr;
-    const bool t_on = rs < rpb;
-    const PostLayout L = post_layout(smem_raw, tpr);
-    // ---- per-chain commands of this tick -> shared memory; snapshot for the Z refill (tick_scalar)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // snapshot, for the Z refill done later in the scalar phase, of the chains that began a transition this tick
     {
         int* const s_new = reinterpret_cast<int*>(smem_raw + kZSnapOffset);
-        for (int cc = tid; cc < tpr; cc += kLikThreads) {
-            const bool run = afl(a, kAfPhase, cc) == kPhaseRun;
-            L.cmd[cc] = make_int4(run ? afl(a, kAfNLvl, cc) : 0, afl(a, kAfLvlMin, cc), run ? afl(a, kAfStoreLevel, cc) : -1, run ? 1 : 0);
-            s_new[cc] = (cc < p.C && run && afl(a, kAfNew, cc) != 0) ? afl(a, kAfDraw, cc) + 1 : -1;
-        }
-        for (int o = tid; o < tpr * 2 * kNutsMaxDepth; o += kLikThreads) L.l_acc[o] = 0.0;
+        for (int cc = threadIdx.x; cc < p.C; cc += kLikThreads)
+            s_new[cc] = (afl(a, kAfPhase, cc) == kPhaseRun && afl(a, kAfNew, cc) != 0) ? afl(a, kAfDraw, cc) + 1 : -1;
     }
-    const bool on = t_on && afl(a, kAfPhase, c) == kPhaseRun;
-    const int dir = afl(a, kAfDir, c), leaf = afl(a, kAfLeaf, c);
-    const bool last = afl(a, kAfLastLeaf, c) != 0;
-    const double h = sc(p, kScH, c);
-    const double* const VAR = slot(p, kSlotVar);
-    double* const PW = slot(p, kSlotPW);
-    const double* const GW = slot(p, kSlotGW);
-    double* const PSR = slot(p, kSlotPSumRun);
-    const double* const PST = slot(p, kSlotPSumTree);
-    const double* const PO = slot(p, dir > 0 ? kSlotPL : kSlotPR);
-    double a_kin = 0.0, a_t0 = 0.0, a_t1 = 0.0;
-    const int rows_per_cta = (p.D + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int r_begin = (int)blockIdx.x * rows_per_cta;
-    const int r_end = min(p.D, r_begin + rows_per_cta);
-    __syncthreads();
     stamp(pt, 8);
-    constexpr int U = 4;    // rows per thread and tile at 64 chains (more chains: fewer rows per thread)
-    const int n_u = (kTileRows + rpb - 1) / rpb;             // core rows per thread and tile (<= U for Cp >= 64)
-    const int buf_doubles = 3 * kTileRows * L.stride;
-    double var[U], gwv[U], pwv[U], psr[U], pstv[U], pov[U];
-
-    // core pass, part 1: all global loads of a tile's rows of this thread (kept in registers)
-    auto core_load = [&](int tile0, int u0) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int rt = rs + (u0 + u) * rpb, d = tile0 + rt;
-            var[u] = gwv[u] = pwv[u] = psr[u] = pstv[u] = pov[u] = 0.0;
-            if (on && rt < kTileRows && d < r_end) {
-                const size_t i = (size_t)d * p.Cp + c;
-                var[u] = VAR[i]; gwv[u] = GW[i]; pwv[u] = PW[i];
-                if (leaf != 0) psr[u] = PSR[i];
-                if (last) { pstv[u] = PST[i]; pov[u] = PO[i]; }
-            }
-        }
-    };
-    // core pass, part 2: half kick, running p_sum, kinetic / whole-tree dots; tile -> shared memory
-    auto core_compute = [&](int tile0, int u0, int buf) {
-        double* const tm = L.t_mom + buf * buf_doubles;
-        double* const tp = L.t_ps + buf * buf_doubles;
-        double* const tv = L.t_var + buf * buf_doubles;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int rt = rs + (u0 + u) * rpb, d = tile0 + rt;
-            if (t_on && rt < kTileRows) {
-                double mom = 0.0, ps = 0.0;
-                if (on && d < r_end) {
-                    const size_t i = (size_t)d * p.Cp + c;
-                    mom = fma(h, gwv[u], pwv[u]);
-                    PW[i] = mom;
-                    const double vel = var[u] * mom;
-                    a_kin = fma(0.5 * vel, mom, a_kin);
-                    ps = psr[u] + mom;
-                    PSR[i] = ps;
-                    if (last) {
-                        const double pst = pstv[u] + ps;
-                        a_t0 = fma(pst, vel, a_t0);
-                        a_t1 = fma(pst, var[u] * pov[u], a_t1);
-                    }
-                }
-                tm[rt * L.stride + c] = mom;     // rows past the end / idle chains: zeros
-                tp[rt * L.stride + c] = ps;
-                tv[rt * L.stride + c] = var[u];
-            }
-        }
-    };
-    // level pass (lane <-> row of the tile, warp <-> chain): 4 chains per warp and round, the
-    // checkpoint loads of all four in flight together (2 levels hoisted, deeper levels are rare)
-    auto level_pass = [&](int tile0, int buf) {
-        const double* const tm = L.t_mom + buf * buf_doubles;
-        const double* const tp = L.t_ps + buf * buf_doubles;
-        const double* const tv = L.t_var + buf * buf_doubles;
-        const int d = tile0 + lane;
-        const bool row_ok = d < r_end;
-        constexpr int J = BGH_POST_J, HL = BGH_POST_HL;
-        auto reduce_add = [&](int cc, int l, double d0, double d1) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                d0 += __shfl_xor_sync(0xffffffffu, d0, o);
-                d1 += __shfl_xor_sync(0xffffffffu, d1, o);
-            }
-            if (lane == 0) {
-                L.l_acc[cc * 2 * kNutsMaxDepth + 2 * l] += d0;
-                L.l_acc[cc * 2 * kNutsMaxDepth + 2 * l + 1] += d1;
-            }
-        };
-        for (int cc0 = warp; cc0 < tpr; cc0 += J * kLikWarps) {
-            int4 cm[J];
-            double mom[J], ps[J], vr[J];
-            double2 ck[J][HL];
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const int cc = cc0 + j * kLikWarps;
-                cm[j] = cc < tpr ? L.cmd[cc] : make_int4(0, 0, -1, 0);
-                mom[j] = ps[j] = vr[j] = 0.0;
-                if (cm[j].w != 0 && (cm[j].x > 0 || cm[j].z >= 0)) {         // warp-uniform
-                    mom[j] = tm[lane * L.stride + cc];
-                    ps[j] = tp[lane * L.stride + cc];
-                    vr[j] = tv[lane * L.stride + cc];
-                    if (cm[j].z >= 0 && row_ok) *ckpt2(p, cm[j].z, d, cc) = make_double2(mom[j], ps[j]);
-                }
-#pragma unroll
-                for (int l = 0; l < HL; ++l) {
-                    ck[j][l] = make_double2(0.0, 0.0);
-                    if (l < cm[j].x && row_ok) ck[j][l] = *ckpt2(p, cm[j].y + l, d, cc);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const int cc = cc0 + j * kLikWarps;
-                const double vel = vr[j] * mom[j];
-#pragma unroll
-                for (int l = 0; l < HL; ++l) {
-                    if (l < cm[j].x) {                                       // warp-uniform
-                        const double pc = ck[j][l].x;
-                        const double sub = ps[j] - ck[j][l].y + pc;          // rows past the end: exactly 0
-                        reduce_add(cc, l, sub * (vr[j] * pc), sub * vel);
-                    }
-                }
-                for (int l = HL; l < cm[j].x; ++l) {
-                    double2 k2 = make_double2(0.0, 0.0);
-                    if (row_ok) k2 = *ckpt2(p, cm[j].y + l, d, cc);
-                    const double sub = ps[j] - k2.y + k2.x;
-                    reduce_add(cc, l, sub * (vr[j] * k2.x), sub * vel);
-                }
-            }
-        }
-    };
-
-    // (a software pipeline over the tiles — core loads of tile t+1 in flight during the level pass of tile t,
-    // two tile buffers — was measured slower: it pushes the kernel over the 128-register budget)
-    for (int tile0 = r_begin; tile0 < r_end; tile0 += kTileRows) {
-        for (int u0 = 0; u0 < n_u; u0 += U) {
-            core_load(tile0, u0);
-            core_compute(tile0, u0, 0);
-        }
+    static_assert(kZSnapOffset + kTickMaxChains * sizeof(int) <= kCmdOffset, "Z snapshot area");
+    const int rpc = (p.D + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int r_begin = (int)blockIdx.x * rpc, r_end = min(p.D, r_begin + rpc);
+    const int trmax = 2 * tile_rows_max(p.Cp);           // only the gradient tile is needed
+    const int n_tiles = (rpc + trmax - 1) / trmax, tr = (rpc + n_tiles - 1) / n_tiles;
+    RowTile T;
+    T.stride = p.Cp + 1;
+    T.tq = nullptr;
+    T.tg = reinterpret_cast<double*>(smem_raw + tile_offset(p.Cp));
+    const double* const GWg = slot(p, kSlotGW);
+    const ChainCmd cm = load_cmd(a, smem_raw);
+    for (int t0 = r_begin; t0 < r_end; t0 += tr) {
+        T.r0 = t0;
+        T.nr = min(tr, r_end - t0);
+        const bool first_tile = t0 == r_begin;
+        tile_load(p, GWg, T.tg, T);
         __syncthreads();
-        level_pass(tile0, 0);
+        for (int c = warp; c < p.C; c += kLikWarps) {
+            if (cm.f(kAfPhase, c) != kPhaseRun) continue;              // warp-uniform
+            const int dir = cm.f(kAfDir, c), leaf = cm.f(kAfLeaf, c), store_level = cm.f(kAfStoreLevel, c);
+            const int lvl_min = cm.f(kAfLvlMin, c), n_lvl = cm.f(kAfNLvl, c);
+            const bool last = cm.f(kAfLastLeaf, c) != 0;
+            const double h = cm.s(kScH, c);
+            switch (n_lvl) {
+                case 0: post_rows<0, 4>(p, T, c, lane, leaf, store_level, lvl_min, last, dir, h, first_tile); break;
+                case 1: post_rows<1, 4>(p, T, c, lane, leaf, store_level, lvl_min, last, dir, h, first_tile); break;
+                case 2: post_rows<2, 2>(p, T, c, lane, leaf, store_level, lvl_min, last, dir, h, first_tile); break;
+                case 3: post_rows<3, 2>(p, T, c, lane, leaf, store_level, lvl_min, last, dir, h, first_tile); break;
+                case 4: post_rows<4, 2>(p, T, c, lane, leaf, store_level, lvl_min, last, dir, h, first_tile); break;
+                case 5: post_rows<5, 1>(p, T, c, lane, leaf, store_level, lvl_min, last, dir, h, first_tile); break;
+                case 6: post_rows<6, 1>(p, T, c, lane, leaf, store_level, lvl_min, last, dir, h, first_tile); break;
+                case 7: post_rows<7, 1>(p, T, c, lane, leaf, store_level, lvl_min, last, dir, h, first_tile); break;
+                case 8: post_rows<8, 1>(p, T, c, lane, leaf, store_level, lvl_min, last, dir, h, first_tile); break;
+                case 9: post_rows<9, 1>(p, T, c, lane, leaf, store_level, lvl_min, last, dir, h, first_tile); break;
+                default: post_rows<10, 1>(p, T, c, lane, leaf, store_level, lvl_min, last, dir, h, first_tile); break;
+            }
+        }
         __syncthreads();
     }
     stamp(pt, 9);
-    // ---- CTA reduction of the three core sums in a fixed order, then the partials of this CTA
-    L.red[0 * kLikThreads + tid] = a_kin;
-    L.red[1 * kLikThreads + tid] = a_t0;
-    L.red[2 * kLikThreads + tid] = a_t1;
-    __syncthreads();
     stamp(pt, 10);
-    for (int o = tid; o < (kAqTree0 + 2) * tpr; o += kLikThreads) {
-        const int k = o / tpr, cc = o % tpr;
-        double t = 0.0;
-        if (k == 0 || k >= kAqTree0) {
-            const int q = k == 0 ? 0 : 1 + (k - kAqTree0);
-            for (int r = 0; r < rpb; ++r) t += L.red[q * kLikThreads + r * tpr + cc];
-        } else {
-            t = L.l_acc[cc * 2 * kNutsMaxDepth + (k - 1)];
-        }
-        p.partials[((size_t)blockIdx.x * kAsyncPartials + k) * p.Cp + cc] = t;
-    }
-    __syncthreads();
 }
-
 
 __device__ __forceinline__ void schedule_leaf_sm(int* fl, int leaf, int depth)
 {
@@ -764,8 +772,8 @@ __device__ __forceinline__ void tick_scalar(const AsyncParams& a, unsigned char*
             const int draw = s_new[cc];
             if (draw < 0 || draw >= a.tune + a.draws) continue;      // CTA-uniform
             const uint2 key = chain_key(p, cc);
-            for (int d = gtid; d < p.D; d += gn)
-                Z[(size_t)d * p.Cp + cc] = momentum_normal(key, draw, (unsigned)(p.coord_offset + d));
+            double* const Zc = Z + (size_t)cc * p.D;                  // chain-major
+            for (int d = gtid; d < p.D; d += gn) Zc[d] = momentum_normal(key, draw, (unsigned)(p.coord_offset + d));
         }
         __syncthreads();   // the snapshot / reduction area is reused below
     }

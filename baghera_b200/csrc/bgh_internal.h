@@ -57,8 +57,9 @@ struct LikParams {
     const double* lp;     //                            sqrt(l)
     const int* gid;
     const int4* groups;   // {a, b, flags, gene id of SNP a}
-    const double* q;      // [D][Cp]
-    double* grad;         // [D][Cp]
+    const double* q;      // element (row d, chain c) at q[d * ds + c * cs]: [D][Cp] (ds = Cp, cs = 1) for the
+    double* grad;         // evaluation API, chain-major [Cp][D] (ds = 1, cs = D) inside the tick kernel
+    long long ds, cs;
     double* slots;        // [2*NG + nCTA][Cp]
     double* part;         // [nCTA][4][Cp]
     double* cc;           // [2][Cp] per-chain constants {1/W^2, mi} written for finalize
@@ -74,8 +75,9 @@ struct LikParams {
 };
 
 struct FinParams {
-    const double* q;
+    const double* q;      // strides as in LikParams
     double* grad;
+    long long ds, cs;
     double* logp;
     const double* slots;
     const double* part;

@@ -52,7 +52,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 __device__ __forceinline__ unsigned long long l2_evict_first_policy()
 {
     unsigned long long pol;
+#ifdef BGH_SNP_EVICT_NORMAL
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+#else
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#endif
     return pol;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, unsigned long long pol)
@@ -179,7 +183,8 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
     const int ra = desc.x, rb = desc.y, flags = desc.z, g_first = desc.w;
     const bool exclusive = (flags & kExclusive) != 0;
     const bool active = ra < rb;
-    const double* const beta = p.q + (size_t)row0 * Cp + ch0;   // per-gene rows (this lane's chains)
+    const long long ds = p.ds, cs = p.cs;
+    const double* const beta = p.q + (long long)row0 * ds + (long long)ch0 * cs;   // per-gene rows (this lane's chains)
 
     const int base0 = ra & ~(CH - 1);   // CH aligned: every bulk copy source is 16-byte aligned
     const int n_chunks = active ? (rb - base0 + CH - 1) / CH : 0;
@@ -208,8 +213,8 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
     if (active && gene_model) {
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
-            braw[k] = beta[(size_t)g_first * Cp + k * CL];
-            bn[k] = (g_first + 1 < p.G) ? beta[(size_t)(g_first + 1) * Cp + k * CL] : 0.0;
+            braw[k] = beta[(long long)g_first * ds + (long long)(k * CL) * cs];
+            bn[k] = (g_first + 1 < p.G) ? beta[(long long)(g_first + 1) * ds + (long long)(k * CL) * cs] : 0.0;
         }
     }
 
@@ -220,21 +225,21 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
         const int ch = ch0 + k * CL;
         if (gamma_model) {
             // ref: gene_regression.py:229-248 — q = [e, mi_logodds__, beta_log__...]
-            const double ev = p.q[0 * Cp + ch];
-            const double xm = p.q[1 * Cp + ch];
+            const double ev = p.q[0 * ds + ch * cs];
+            const double xm = p.q[1 * ds + ch * cs];
             iW2[k] = 0.0;
             mi[k] = sigmoid_d(xm);
             ne[k] = p.fix ? -1.0 : -ev;              // ref: gene_regression.py:234-240
         } else if (gene_model) {
-            const double xW = p.q[0 * Cp + ch];
-            const double ev = p.q[1 * Cp + ch];
-            const double xm = p.q[2 * Cp + ch];
+            const double xW = p.q[0 * ds + ch * cs];
+            const double ev = p.q[1 * ds + ch * cs];
+            const double xm = p.q[2 * ds + ch * cs];
             iW2[k] = exp(-2.0 * xW);
             mi[k] = sigmoid_d(xm);
             ne[k] = p.fix ? -1.0 : -ev;              // ref: gene_regression.py:85-90
         } else {
-            const double x0 = p.q[0 * Cp + ch];
-            const double xm = p.q[1 * Cp + ch];
+            const double x0 = p.q[0 * ds + ch * cs];
+            const double xm = p.q[1 * ds + ch * cs];
             iW2[k] = 0.0;
             mi[k] = sigmoid_d(xm);
             ne[k] = p.fix ? -(kGwFixLo + (kGwFixHi - kGwFixLo) * sigmoid_d(x0)) : -x0;
@@ -272,7 +277,7 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
 #pragma unroll
             for (int k = 0; k < CPL; ++k) {
                 if (gene_model)
-                    dst[k] = (g < p.G) ? beta[(size_t)g * Cp + k * CL] : 0.0;
+                    dst[k] = (g < p.G) ? beta[(long long)g * ds + (long long)(k * CL) * cs] : 0.0;
                 else
                     dst[k] = mi[k];
             }
@@ -294,13 +299,13 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
                     for (int k = 0; k < CPL; ++k) dst[k * CL] = ag[k];
                 } else if (gamma_model) {
                     // d/d beta_log = beta (c sum r - rate) + mi       (prior + log-Jacobian + likelihood)
-                    double* dst = p.grad + (size_t)(row0 + cur) * Cp + ch0;
+                    double* dst = p.grad + (long long)(row0 + cur) * ds + (long long)ch0 * cs;
 #pragma unroll
-                    for (int k = 0; k < CPL; ++k) dst[k * CL] = fma(nb[k] * neg_inv_c, fma(p.c, ag[k], -p.gamma_rate), mi[k]);
+                    for (int k = 0; k < CPL; ++k) dst[(long long)(k * CL) * cs] = fma(nb[k] * neg_inv_c, fma(p.c, ag[k], -p.gamma_rate), mi[k]);
                 } else if (gene_model) {
-                    double* dst = p.grad + (size_t)(row0 + cur) * Cp + ch0;
+                    double* dst = p.grad + (long long)(row0 + cur) * ds + (long long)ch0 * cs;
 #pragma unroll
-                    for (int k = 0; k < CPL; ++k) dst[k * CL] = fma(p.c, ag[k], -db[k] * iW2[k]);
+                    for (int k = 0; k < CPL; ++k) dst[(long long)(k * CL) * cs] = fma(p.c, ag[k], -db[k] * iW2[k]);
                 }
                 owner = !to_head;   // this group holds the gene's first SNP: it owns the prior terms
             }

@@ -648,7 +648,7 @@ __global__ void nuts_async_zgen_kernel(const AsyncParams a)
     double* const Z = slot(p, kSlotZ);
     const size_t n = (size_t)p.D * p.Cp;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const int d = (int)(i / p.Cp), c = (int)(i % p.Cp);
+        const int c = (int)(i / p.D), d = (int)(i % p.D);     // chain-major, as the tick kernel keeps its state
         Z[i] = momentum_normal(chain_key(p, c), 0, (unsigned)(p.coord_offset + d));
     }
 }

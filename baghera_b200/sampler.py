@@ -144,12 +144,15 @@ class NutsSampler:
         dt = trace_dtype or t.float64
         if dt not in (t.float64, t.float32):
             raise ValueError("trace dtype must be float64 or float32")
-        trace = t.empty((max(draws, 1), eng.D, C), dtype=dt, device=eng.device)
+        # the device writes the trace chain-major [draws, C, D] (contiguous per chain); callers see the
+        # reference-shaped view [draws, D, C]
+        trace_cd = t.empty((max(draws, 1), C, eng.D), dtype=dt, device=eng.device)
+        trace = trace_cd.permute(0, 2, 1)
         stats = t.zeros((tune + draws, NUTS_N_STATS, C), dtype=t.float64, device=eng.device)
         ab = bgh_nuts_async_buffers()
         ab.base = self.buf
         ab.afl = self.afl.data_ptr()
-        ab.trace = trace.data_ptr()
+        ab.trace = trace_cd.data_ptr()
         ab.run_stats = stats.data_ptr()
         ab.trace_f32 = int(dt == t.float32)
         n_ticks = ctypes.c_int64(0)

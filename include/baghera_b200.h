@@ -261,7 +261,10 @@ int bgh_nuts_stop_tuning(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nu
  * Buffers: as bgh_nuts_buffers, but sc has BGH_NUTS_ASYNC_N_SC rows and partials
  * BGH_NUTS_ASYNC_PARTIALS quantities per block; plus
  *   afl      int32[BGH_NUTS_ASYNC_N_FL][Cp]
- *   trace    [draws][D][C] fp64 (trace_f32 = 0) or fp32: positions after each post-tuning transition
+ *   trace    [draws][C][D] fp64 (trace_f32 = 0) or fp32: positions after each post-tuning transition
+ *            (chain-major: inside the run the state is kept chain-major so that every per-chain vector
+ *            operation of the tree bookkeeping is a contiguous stream; Q / GRAD / VAR and the adaptation
+ *            slots are converted from and back to the [D][Cp] layout at the start / end of the call)
  *   stats    double[tune + draws][BGH_NUTS_N_STATS][C]
  * Call bgh_nuts_init first (start point, mass-matrix slots); then bgh_nuts_run once. */
 typedef struct bgh_nuts_async_buffers {
