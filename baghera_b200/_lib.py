@@ -134,7 +134,7 @@ _LIB = None
 
 def build(verbose: bool = False) -> str:
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    out = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
+    out = subprocess.run(["make", "-j4", "-C", CSRC], capture_output=True, text=True)
     if out.returncode != 0:
         raise RuntimeError("building libbaghera_b200.so failed:\n" + out.stdout + out.stderr)
     if verbose:

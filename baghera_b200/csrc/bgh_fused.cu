@@ -212,7 +212,7 @@ __device__ __forceinline__ void fin_phase(const FinParams& p, unsigned char* sme
 // ---------------------------------------------------------------------------------------------
 // one launch per evaluation
 // ---------------------------------------------------------------------------------------------
-template <int CL, int CPL>
+template <int CL, int CPL, bool GAMMA>
 __global__ void __launch_bounds__(kLikThreads, 1) logp_grad_fused_kernel(const FusedParams f)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kLikThreads, 1) logp_grad_fused_kernel(const F
     __syncthreads();
     uint32_t par = 0;
     unsigned long long target = f.bar_base;
-    for (int cb = 0; cb < f.chain_blocks; ++cb) lik_phase<CL, CPL>(f.lik, smem_raw, blockIdx.x, cb, par);
+    for (int cb = 0; cb < f.chain_blocks; ++cb) lik_phase<CL, CPL, GAMMA>(f.lik, smem_raw, blockIdx.x, cb, par);
     grid_barrier(f.bar, target, f.status);
     fin_phase(f.fin, smem_raw);
 }
@@ -287,7 +287,7 @@ __device__ __forceinline__ void peer_allreduce(const PeerParams& pr, double* pay
     __syncthreads();
 }
 
-template <int CL, int CPL>
+template <int CL, int CPL, bool GAMMA>
 __global__ void __launch_bounds__(kLikThreads, 1) logp_grad_sharded_kernel(const FusedParams f, const PeerParams pr)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(kLikThreads, 1) logp_grad_sharded_kernel(const
     __syncthreads();
     uint32_t par = 0;
     unsigned long long target = f.bar_base;
-    for (int cb = 0; cb < f.chain_blocks; ++cb) lik_phase<CL, CPL>(f.lik, smem_raw, blockIdx.x, cb, par);
+    for (int cb = 0; cb < f.chain_blocks; ++cb) lik_phase<CL, CPL, GAMMA>(f.lik, smem_raw, blockIdx.x, cb, par);
     grid_barrier(f.bar, target, f.status);
     fin_phase(f.fin, smem_raw);            // finish_inline == 0: payload rows + local split genes
     grid_barrier(f.bar, target, f.status);
@@ -967,7 +967,7 @@ __device__ __forceinline__ void tick_scalar(const AsyncParams& a, unsigned char*
     }
 }
 
-template <int CL, int CPL>
+template <int CL, int CPL, bool GAMMA>
 __global__ void __launch_bounds__(kLikThreads, 1) nuts_tick_kernel(const TickParams t)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -991,7 +991,7 @@ __global__ void __launch_bounds__(kLikThreads, 1) nuts_tick_kernel(const TickPar
         grid_barrier(f.bar, target, f.status);
         fence_proxy_async();   // the staging area was written through the generic proxy (reductions)
         BGH_PHASE_STAMP(2);
-        for (int cb = 0; cb < f.chain_blocks; ++cb) lik_phase<CL, CPL>(f.lik, smem_raw, blockIdx.x, cb, par);
+        for (int cb = 0; cb < f.chain_blocks; ++cb) lik_phase<CL, CPL, GAMMA>(f.lik, smem_raw, blockIdx.x, cb, par);
         BGH_PHASE_STAMP(3);
         grid_barrier(f.bar, target, f.status);
         fin_phase(f.fin, smem_raw);
@@ -1019,12 +1019,16 @@ __global__ void __launch_bounds__(kLikThreads, 1) nuts_tick_kernel(const TickPar
 template <int CL, int CPL>
 static cudaError_t configure_fused_t()
 {
-    cudaError_t e = cudaFuncSetAttribute(logp_grad_fused_kernel<CL, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kLikSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(logp_grad_sharded_kernel<CL, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLikSmemBytes);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(nuts_tick_kernel<CL, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLikSmemBytes);
+    cudaError_t e = cudaSuccess;
+    auto set = [&](const void* f) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLikSmemBytes);
+    };
+    set((const void*)logp_grad_fused_kernel<CL, CPL, false>);
+    set((const void*)logp_grad_fused_kernel<CL, CPL, true>);
+    set((const void*)logp_grad_sharded_kernel<CL, CPL, false>);
+    set((const void*)nuts_tick_kernel<CL, CPL, false>);
+    set((const void*)nuts_tick_kernel<CL, CPL, true>);
+    return e;
 }
 
 cudaError_t fused_configure()
@@ -1042,22 +1046,24 @@ template <int CL, int CPL>
 static cudaError_t launch_fused_t(const FusedParams& f, int n_cta, cudaStream_t s)
 {
     void* args[] = {const_cast<FusedParams*>(&f)};
-    return cudaLaunchCooperativeKernel((const void*)logp_grad_fused_kernel<CL, CPL>, dim3(n_cta), dim3(kLikThreads), args,
-                                       kLikSmemBytes, s);
+    const void* fn = f.lik.model == BGH_MODEL_GENE_GAMMA ? (const void*)logp_grad_fused_kernel<CL, CPL, true>
+                                                         : (const void*)logp_grad_fused_kernel<CL, CPL, false>;
+    return cudaLaunchCooperativeKernel(fn, dim3(n_cta), dim3(kLikThreads), args, kLikSmemBytes, s);
 }
 template <int CL, int CPL>
 static cudaError_t launch_sharded_t(const FusedParams& f, const PeerParams& pr, int n_cta, cudaStream_t s)
 {
     void* args[] = {const_cast<FusedParams*>(&f), const_cast<PeerParams*>(&pr)};
-    return cudaLaunchCooperativeKernel((const void*)logp_grad_sharded_kernel<CL, CPL>, dim3(n_cta), dim3(kLikThreads), args,
-                                       kLikSmemBytes, s);
+    return cudaLaunchCooperativeKernel((const void*)logp_grad_sharded_kernel<CL, CPL, false>, dim3(n_cta), dim3(kLikThreads), args,
+                                       kLikSmemBytes, s);     // the gamma model runs on single-rank contexts
 }
 template <int CL, int CPL>
 static cudaError_t launch_tick_t(const TickParams& t, int n_cta, cudaStream_t s)
 {
     void* args[] = {const_cast<TickParams*>(&t)};
-    return cudaLaunchCooperativeKernel((const void*)nuts_tick_kernel<CL, CPL>, dim3(n_cta), dim3(kLikThreads), args,
-                                       kLikSmemBytes, s);
+    const void* fn = t.f.lik.model == BGH_MODEL_GENE_GAMMA ? (const void*)nuts_tick_kernel<CL, CPL, true>
+                                                           : (const void*)nuts_tick_kernel<CL, CPL, false>;
+    return cudaLaunchCooperativeKernel(fn, dim3(n_cta), dim3(kLikThreads), args, kLikSmemBytes, s);
 }
 
 cudaError_t launch_logp_grad_fused(const FusedParams& f, int CL, int CPL, int n_cta, cudaStream_t s)

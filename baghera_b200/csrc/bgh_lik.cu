@@ -21,14 +21,14 @@ namespace bgh {
 // ---------------------------------------------------------------------------------------------
 size_t lik_smem_bytes() { return kLikSmemBytes; }
 
-template <int CL, int CPL>
+template <int CL, int CPL, bool GAMMA>
 __global__ void __launch_bounds__(kLikThreads, 1) lik_kernel(const LikParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     lik_stage_init(smem_raw);
     __syncthreads();
     uint32_t par = 0;
-    lik_phase<CL, CPL>(p, smem_raw, blockIdx.x, blockIdx.y, par);
+    lik_phase<CL, CPL, GAMMA>(p, smem_raw, blockIdx.x, blockIdx.y, par);
 }
 
 // log(sigmoid(x)) and log(1 - sigmoid(x)) without cancellation
@@ -238,15 +238,20 @@ template <int CL, int CPL>
 static cudaError_t launch_lik_t(const LikParams& p, int n_cta, int chain_blocks, cudaStream_t s)
 {
     dim3 grid(n_cta, chain_blocks);
-    lik_kernel<CL, CPL><<<grid, kLikThreads, lik_smem_bytes(), s>>>(p);
+    if (p.model == BGH_MODEL_GENE_GAMMA)
+        lik_kernel<CL, CPL, true><<<grid, kLikThreads, lik_smem_bytes(), s>>>(p);
+    else
+        lik_kernel<CL, CPL, false><<<grid, kLikThreads, lik_smem_bytes(), s>>>(p);
     return cudaGetLastError();
 }
 
 template <int CL, int CPL>
 static cudaError_t configure_t()
 {
-    return cudaFuncSetAttribute(lik_kernel<CL, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)lik_smem_bytes());
+    cudaError_t e = cudaFuncSetAttribute(lik_kernel<CL, CPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)lik_smem_bytes());
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(lik_kernel<CL, CPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lik_smem_bytes());
 }
 
 cudaError_t lik_configure()

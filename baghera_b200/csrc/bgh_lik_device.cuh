@@ -148,7 +148,7 @@ __device__ __forceinline__ unsigned sm_id()
 // (bit s = parity the next wait on stage s expects); start it at 0 right after lik_stage_init.
 // Must be called by all kLikThreads threads of the CTA (contains CTA barriers).
 // ---------------------------------------------------------------------------------------------
-template <int CL, int CPL>
+template <int CL, int CPL, bool GAMMA>
 __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* smem_raw, const int cta, const int chain_block,
                                           uint32_t& par)
 {
@@ -168,7 +168,7 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
     const int v = (cta * kLikWarps + warp) * SL + grp;
     const int Cp = p.Cp;
     const int ch0 = chain_block * CG + lc;   // chain of slot k is ch0 + k*CL
-    const bool gamma_model = p.model == BGH_MODEL_GENE_GAMMA;
+    constexpr bool gamma_model = GAMMA;     // compile-time: keeps exp() and the extra selects out of the normal model's code
     const bool gene_model = p.model == BGH_MODEL_GENE_NORMAL || gamma_model;
     const int row0 = gamma_model ? 2 : 3;   // first per-gene row of q / grad
 
