@@ -21,7 +21,7 @@ namespace bgh {
 // ---------------------------------------------------------------------------------------------
 int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_cta, int groups_per_cta,
                bool first_partial, bool last_partial, int first_row, int last_row, double kappa,
-               Plan* plan, std::string* err)
+               Plan* plan, std::string* err, int align)
 {
     const int n_groups = n_cta * groups_per_cta;
     if (M < 0 || M > 0x7fffff00LL || n_cta <= 0 || groups_per_cta <= 0 || G <= 0) {
@@ -194,6 +194,22 @@ int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_cta, int groups_p
         P.off[(size_t)v0] = (int32_t)r.b;
     }
     P.off[(size_t)n_groups] = (int32_t)M;
+    if (align > 1) {
+        // batch-aligned ranges: a cut inside a gene moves down to a multiple of `align` (gene boundaries of the
+        // padded array are multiples already); monotonicity is preserved by rounding down
+        for (int v = 1; v < n_groups; ++v) P.off[(size_t)v] = (P.off[(size_t)v] / align) * align;
+        // the owner of an exclusive gene's prior terms is its first NON-EMPTY group: recompute (tiny inputs can
+        // lose a group to the rounding)
+        int32_t owned_gene = -1;
+        for (int v = 0; v < n_groups; ++v) {
+            if (!(P.flags[(size_t)v] & kExclusive)) continue;
+            P.flags[(size_t)v] &= ~kOwner;
+            if (P.off[(size_t)v] >= P.off[(size_t)v + 1]) continue;
+            const int32_t g = gid[P.off[(size_t)v]];
+            if (g != owned_gene && !(g == 0 && first_partial)) P.flags[(size_t)v] |= kOwner;
+            owned_gene = g;
+        }
+    }
 
     // flags + slot lists of the mixed groups, mirroring the kernel's flush rule
     std::vector<std::pair<int32_t, int32_t>> mixed_slots;   // (gene, slot)
@@ -335,7 +351,7 @@ static double plan_kappa()
 {
     const char* e = getenv("BGH_PLAN_KAPPA");
     if (e && *e) return atof(e);
-    return 10.0;
+    return 5.0;     // a gene boundary (flush + slope switch in front of a batch) costs about 5 SNPs' worth (measured)
 }
 
 static void pick_chain_geometry(int C, int* CL, int* CPL, int* Cp)
@@ -556,34 +572,42 @@ int bgh_upload(bgh_ctx* ctx, const float* chi2, const float* ld, const int32_t* 
         cnt[1] = M;
     }
     for (int32_t g = 0; g < G; ++g) cnt[(size_t)g + 1] += cnt[g];
-    const int64_t Mpad = ((M + kChunk - 1) / kChunk) * kChunk + kChunk;
-    std::vector<float> s_sorted((size_t)Mpad, 0.0f), l_sorted((size_t)Mpad, 1.0f);
+    // Every gene is padded to a multiple of the kernel's batch (kLikBatch SNPs) with zero-weight SNPs
+    // (sp = wp = lp = 0 -> rho = 0: they add exactly nothing), so a batch never straddles a gene boundary
+    // and the inner loop needs no per-SNP boundary handling.  Mp = padded SNP count.
+    std::vector<int64_t> pcnt((size_t)G + 1, 0);
+    for (int32_t g = 0; g < G; ++g) {
+        const int64_t n = cnt[(size_t)g + 1] - cnt[g];
+        pcnt[(size_t)g + 1] = pcnt[g] + ((n + kLikBatch - 1) / kLikBatch) * kLikBatch;
+    }
+    const int64_t Mp = pcnt[(size_t)G];
+    if (Mp > 0x7fffff00LL) return fail(ctx, BGH_EINVAL, "bgh_upload: too many SNPs after padding");
+    const int64_t Mpad = ((Mp + kChunk - 1) / kChunk) * kChunk + kChunk;
+    std::vector<float> s_sorted((size_t)Mpad, 0.0f), l_sorted((size_t)Mpad, 0.0f);   // l = 0 marks padding
     std::vector<int32_t> g_sorted((size_t)Mpad, G - 1);
+    for (int32_t g = 0; g < G; ++g)
+        for (int64_t j = pcnt[g]; j < pcnt[(size_t)g + 1]; ++j) g_sorted[(size_t)j] = g;
     {
-        std::vector<int64_t> pos(cnt.begin(), cnt.end() - 1);
+        std::vector<int64_t> pos(pcnt.begin(), pcnt.end() - 1);
         for (int64_t j = 0; j < M; ++j) {
             const int32_t g = gene_id ? gene_id[j] : 0;
             const int64_t d = pos[(size_t)g]++;
+            if (!(ld[j] > 0.0f) || !isfinite(ld[j]) || !isfinite(chi2[j]))
+                return fail(ctx, BGH_EINVAL, "bgh_upload: ld must be finite and > 0, chi2 finite (snps.py:121 gives l >= 1)");
             s_sorted[(size_t)d] = chi2[j];
             l_sorted[(size_t)d] = ld[j];
-            g_sorted[(size_t)d] = g;
         }
     }
     double acc = 0.0;
-    for (int64_t j = 0; j < M; ++j) {
-        const float l = l_sorted[(size_t)j];
-        if (!(l > 0.0f) || !isfinite(l) || !isfinite(s_sorted[(size_t)j]))
-            return fail(ctx, BGH_EINVAL, "bgh_upload: ld must be finite and > 0, chi2 finite (snps.py:121 gives l >= 1)");
-        acc += log((double)l);
-    }
+    for (int64_t j = 0; j < M; ++j) acc += log((double)ld[j]);
     ctx->lik_const = -0.5 * acc - 0.5 * (double)M * kLog2Pi;
 
     const bool gw = ctx->cfg.model == BGH_MODEL_GW_NORMAL;
     const bool fp = gw ? true : ctx->cfg.first_gene_partial != 0;
     const bool lp = gw ? true : ctx->cfg.last_gene_partial != 0;
     std::string err;
-    int rc = build_plan(M, g_sorted.data(), G, ctx->n_cta, kLikWarps * (32 / ctx->CL), fp, lp, ctx->cfg.first_gene_row,
-                        ctx->cfg.last_gene_row, plan_kappa(), &ctx->plan, &err);
+    int rc = build_plan(Mp, g_sorted.data(), G, ctx->n_cta, kLikWarps * (32 / ctx->CL), fp, lp, ctx->cfg.first_gene_row,
+                        ctx->cfg.last_gene_row, plan_kappa(), &ctx->plan, &err, kLikBatch);
     if (rc != BGH_OK) return fail(ctx, rc, err);
 
     auto dfree = [](auto*& p) { cudaFree(p); p = nullptr; };
@@ -618,7 +642,7 @@ int bgh_upload(bgh_ctx* ctx, const float* chi2, const float* ld, const int32_t* 
         for (int which = 0; which < 3; ++which) {
             for (int64_t j = 0; j < Mpad; ++j) {
                 const double l = (double)l_sorted[(size_t)j], sq = sqrt(l);
-                prep[(size_t)j] = which == 0 ? (double)s_sorted[(size_t)j] / sq : (which == 1 ? 1.0 / sq : sq);
+                prep[(size_t)j] = l > 0.0 ? (which == 0 ? (double)s_sorted[(size_t)j] / sq : (which == 1 ? 1.0 / sq : sq)) : 0.0;
             }
             double* dst = which == 0 ? ctx->d_xs : (which == 1 ? ctx->d_xw : ctx->d_xl);
             BGH_CUDA(ctx, cudaMemcpy(dst, prep.data(), sizeof(double) * (size_t)Mpad, cudaMemcpyHostToDevice));

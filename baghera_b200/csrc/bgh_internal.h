@@ -47,9 +47,11 @@ struct Plan {
 };
 
 // gid must be sorted ascending.  Returns 0 or BGH_EINVAL (message in err).
+// `align` > 1: every range boundary that is not a gene boundary is rounded down to a multiple of `align`
+// (the upload pads every gene to a multiple of the kernel's batch, so gene boundaries already are).
 int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_cta, int groups_per_cta,
                bool first_partial, bool last_partial, int first_row, int last_row, double kappa,
-               Plan* plan, std::string* err);
+               Plan* plan, std::string* err, int align = 1);
 
 struct LikParams {
     const double* sp;     // prepared SoA, gene sorted: s / sqrt(l)

@@ -349,10 +349,13 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
             mbar_wait(bar0 + 64u * st, (par >> st) & 1u);
             par ^= 1u << st;
 
-            // one SNP with the gene-boundary check (tail of a chunk / several boundaries in a batch)
-            auto step_checked = [&](int i) {
+            // The upload pads every gene to a multiple of B SNPs (zero-weight padding) and the plan cuts
+            // ranges at multiples of B: a batch never straddles a gene boundary, so the only boundary work
+            // is "flush the finished gene, switch the slope" in front of a batch.
+            const int i1 = min(rb - base, CH);
+            for (int i = max(ra - base, 0); i < i1; i += B) {
                 const int g_i = sm_g[i];
-                if (g_i != cur) {
+                if (g_i != cur) {                                   // group-uniform
                     flush(false);
 #pragma unroll
                     for (int k = 0; k < CPL; ++k) ag[k] = 0.0;
@@ -365,77 +368,19 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
                     }
                     enter_gene(g_i, tmp);
                 }
-                accumulate(sm_s[i], sm_w[i], sm_l[i]);
-            };
-
-            int i = max(ra - base, 0);
-            const int i1 = min(rb - base, CH);
-            // batches are B aligned (vector LDS); a range that starts mid-batch steps up to the boundary
-            for (; i < i1 && (i & (B - 1)) != 0; ++i) step_checked(i);
-            while (i + B <= i1) {
-                // SNPs are gene sorted: if the last SNP of the batch is still in `cur`, all of it is
-                const int g_last = sm_g[i + B - 1];
-                if (g_last == cur) {
-                    double2 s2v[B / 2], w2v[B / 2], l2v[B / 2];
+                double2 s2v[B / 2], w2v[B / 2], l2v[B / 2];
 #pragma unroll
-                    for (int t = 0; t < B / 2; ++t) {
-                        s2v[t] = *reinterpret_cast<const double2*>(sm_s + i + 2 * t);
-                        w2v[t] = *reinterpret_cast<const double2*>(sm_w + i + 2 * t);
-                        l2v[t] = *reinterpret_cast<const double2*>(sm_l + i + 2 * t);
-                    }
-#pragma unroll
-                    for (int t = 0; t < B / 2; ++t) {
-                        accumulate(s2v[t].x, w2v[t].x, l2v[t].x);
-                        accumulate(s2v[t].y, w2v[t].y, l2v[t].y);
-                    }
-                    i += B;
-                    continue;
+                for (int t = 0; t < B / 2; ++t) {
+                    s2v[t] = *reinterpret_cast<const double2*>(sm_s + i + 2 * t);
+                    w2v[t] = *reinterpret_cast<const double2*>(sm_w + i + 2 * t);
+                    l2v[t] = *reinterpret_cast<const double2*>(sm_l + i + 2 * t);
                 }
-                // at least one gene boundary inside the batch: nlead SNPs still belong to `cur`
-                int nlead = 0;
 #pragma unroll
-                for (int t = 0; t < B - 1; ++t) nlead += (sm_g[i + t] == cur) ? 1 : 0;
-                if (sm_g[i + nlead] == g_last) {
-                    // exactly one boundary: [0,nlead) -> cur, [nlead,B) -> g_last. The two per-chain
-                    // sums that do not depend on the gene (ae, al) run straight through; only the
-                    // slope and the per-gene accumulator are selected per SNP.
-                    double raw2[CPL], nb2[CPL], ag2[CPL];
-                    if (g_last == cur + 1) {
-#pragma unroll
-                        for (int k = 0; k < CPL; ++k) raw2[k] = bn[k];
-                    } else {
-                        load_beta(g_last, raw2);
-                    }
-#pragma unroll
-                    for (int k = 0; k < CPL; ++k) {
-                        nb2[k] = -p.c * (gamma_model ? exp(raw2[k]) : raw2[k]);
-                        ag2[k] = 0.0;
-                    }
-#pragma unroll
-                    for (int t = 0; t < B; ++t) {
-                        const double spv = sm_s[i + t], wpv = sm_w[i + t], lpv = sm_l[i + t];
-                        const bool lead = t < nlead;
-#pragma unroll
-                        for (int k = 0; k < CPL; ++k) {
-                            const double rho = fma(lead ? nb[k] : nb2[k], lpv, fma(ne[k], wpv, spv));
-                            if (lead) ag[k] = fma(rho, lpv, ag[k]); else ag2[k] = fma(rho, lpv, ag2[k]);
-                            ae[k] = fma(rho, wpv, ae[k]);
-                            al[k] = fma(rho, rho, al[k]);
-                        }
-                    }
-                    flush(false);
-#pragma unroll
-                    for (int k = 0; k < CPL; ++k) ag[k] = ag2[k];
-                    enter_gene(g_last, raw2);
-                    i += B;
-                } else {
-                    // several boundaries (genes shorter than a batch): step through the whole batch so
-                    // that the next one stays B aligned
-                    for (int t = 0; t < B; ++t) step_checked(i + t);
-                    i += B;
+                for (int t = 0; t < B / 2; ++t) {
+                    accumulate(s2v[t].x, w2v[t].x, l2v[t].x);
+                    accumulate(s2v[t].y, w2v[t].y, l2v[t].y);
                 }
             }
-            for (; i < i1; ++i) step_checked(i);
             __syncwarp(gmask);
             if (lc == 0 && kc + kStages < n_chunks) issue(kc + kStages);
         }

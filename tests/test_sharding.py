@@ -173,3 +173,40 @@ def test_emulated_ranks_on_one_gpu(world, M, G):
         assert grad_rel_err(g_all[i], g_ref[i]) < REL_TOL
     for e in engines:
         e.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 8])
+def test_gw_model_emulated_ranks(world):
+    """cfg5 shape (genome-wide model, ref: heritability.py:44-55) sharded by SNP ranges: the single slope's
+    residual sum is the rank-shared payload row."""
+    import torch
+    from baghera_b200.engine import Engine
+    d = synth.make_arrays(400_000, 1)
+    C = 8
+    Q = synth.jittered_start(2, C, seed=9, model="gw")
+    gid = np.zeros(d.M, dtype=np.int32)
+    shards = [shard_dataset(d.chi2, d.ld, gid, 1, r, world) for r in range(world)]
+    engines = [Engine(s.chi2, s.ld, None, 1, d.c, C, model="gw", shard=s.cfg) for s in shards]
+    Cp, rows = engines[0].Cp, engines[0].payload_rows
+    assert rows == 5
+    qs = [e.to_device_layout(Q) for e in engines]
+    grads = [torch.zeros_like(q) for q in qs]
+    payloads = [torch.zeros((rows, Cp), dtype=torch.float64, device="cuda") for _ in range(world)]
+    for e, q, g, p in zip(engines, qs, grads, payloads):
+        e.logp_grad_local(q, g, p)
+    total = torch.stack(payloads).sum(dim=0)
+    const = sum(e.lik_const for e in engines)
+    chi2, ld = d.chi2.astype(np.float64), d.ld.astype(np.float64)
+    for e, q, g in zip(engines, qs, grads):
+        e.set_lik_const(const)
+        lp = torch.empty(Cp, dtype=torch.float64, device="cuda")
+        e.logp_grad_finish(q, total, lp, g)
+        torch.cuda.synchronize()
+        gg = e.from_device_layout(g).cpu().numpy()
+        for i in range(C):
+            lp_ref, g_ref = mo.gw_logp_grad_closed(Q[i], chi2, ld, d.c)
+            assert abs(lp[i].item() - lp_ref) <= REL_TOL * abs(lp_ref)
+            assert grad_rel_err(gg[i], g_ref) <= REL_TOL
+    for e in engines:
+        e.close()
