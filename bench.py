@@ -28,6 +28,8 @@ WORKLOADS = {
     "cfg3": dict(M=1_100_000, G=15_000, C=64, desc="UKBB-shaped synthetic 1.1M SNPs x 15k genes, 64 chains, normal model"),
     "cfg2": dict(M=1_100_000, G=15_000, C=4, desc="UKBB-shaped synthetic 1.1M SNPs x 15k genes, 4 chains, normal model"),
     "cfg1": dict(M=20_000, G=200, C=4, desc="synthetic 20k SNPs x 200 genes, 4 chains, normal model"),
+    "cfg5": dict(M=10_000_000, G=1, C=64, model="gw",
+                 desc="genome-wide model (single h2 + intercept) on a 10M imputed-SNP synthetic set, 64 chains"),
 }
 
 
@@ -202,19 +204,25 @@ def bench_gpu(args, wl):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     M, G, C = wl["M"], wl["G"], wl["C"]
+    model = wl.get("model", "gene")
+    gw = model == "gw"
+    if gw:
+        args.no_sampler = True          # the ESS/s section and the CPU port are for the gene-level model
+        args.no_cpu_baseline = True
     d = synth.make_arrays(M, G)
-    D = G + 3
-    Q = synth.jittered_start(D, C, seed=1)
+    D = 2 if gw else G + 3
+    Q = synth.jittered_start(D, C, seed=1, model=model)
+    gid = np.zeros(M, dtype=np.int32) if gw else d.gene_id
 
     if world == 1:
-        eng = Engine(d.chi2, d.ld, d.gene_id, G, d.c, C, device=local_rank)
+        eng = Engine(d.chi2, d.ld, None if gw else gid, G, d.c, C, model=model, device=local_rank)
         q_dev = eng.to_device_layout(Q)
         g_lo = 0
     else:
         from baghera_b200.sharding import shard_dataset
-        sh = shard_dataset(d.chi2, d.ld, d.gene_id, G, rank, world)
-        eng = Engine(sh.chi2, sh.ld, sh.gene_id, sh.n_genes, d.c, C, device=local_rank, shard=sh.cfg)
-        q_dev = eng.to_device_layout(sh.local_q(Q))
+        sh = shard_dataset(d.chi2, d.ld, gid, G, rank, world)
+        eng = Engine(sh.chi2, sh.ld, None if gw else sh.gene_id, sh.n_genes, d.c, C, model=model, device=local_rank, shard=sh.cfg)
+        q_dev = eng.to_device_layout(Q if gw else sh.local_q(Q))
         lc = torch.tensor([eng.lik_const], dtype=torch.float64, device=dev)
         dist.all_reduce(lc)
         eng.set_lik_const(float(lc.item()))
@@ -296,7 +304,7 @@ def bench_gpu(args, wl):
         lik_ms = prof_lik / max(prof_n, 1)
         fin_ms = prof_fin / max(prof_n, 1)
         Ml, Dl = eng.M, eng.D
-        b_alg = 12.0 * Ml + 16.0 * C * Dl + 8.0 * C           # SNP stream + read q + write grad + logp
+        b_alg = (8.0 if gw else 12.0) * Ml + 16.0 * C * Dl + 8.0 * C   # SNP stream (no gene id in the gw model) + q + grad + logp
         achieved = b_alg / (lik_ms * 1e-3) / 1e9 if lik_ms > 0 else 0.0
         dp_instr = 5.0 * Ml * C                               # 5 DFMA per (SNP, chain): bgh_lik_device.cuh
         try:
@@ -400,8 +408,8 @@ def main():
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
-        if args.steps > 50:
-            args.steps = 50          # each step is ~1 s of CPU work at full size; keep the run bounded
+        if args.steps > 5000:
+            args.steps = 5000        # a step is ~7 ms (one chain-eval per host thread in parallel); keep the run bounded
         bench_reference(args, wl)
     else:
         bench_gpu(args, wl)

@@ -36,10 +36,10 @@ def test_plan_balance_and_snapping(built_lib):
     plan = debug_plan(gid, 15_000, 148, 16)
     lens = np.diff(plan["off"])
     ideal = 1_100_000 / NG
-    # the plan balances cost = SNPs + kappa * gene boundaries (kappa = 10 SNP-equivalents per flush)
+    # the plan balances cost = SNPs + kappa * gene boundaries (kappa = 5 SNP-equivalents per flush, plan_kappa in bgh_api.cu)
     starts = np.flatnonzero(np.diff(gid, prepend=-1))
     n_starts = np.diff(np.searchsorted(starts, plan["off"]))
-    cost = lens + 10.0 * n_starts
+    cost = lens + 5.0 * n_starts
     excl_ = (plan["flags"] & 4) != 0
     cost[excl_] = lens[excl_]
     assert cost.max() <= 1.15 * cost.mean() and cost.min() >= 0.85 * cost.mean()
