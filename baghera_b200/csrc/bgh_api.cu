@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <new>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -311,15 +312,15 @@ struct bgh_ctx {
     int peer_rank = -1, peer_world = 0;
     unsigned long long peer_epoch = 0;
     // host-entry staging (lazily allocated)
-    static constexpr int kPipe = 2;
-    double* d_q_cd[kPipe] = {nullptr, nullptr};
-    double* d_q_dc[kPipe] = {nullptr, nullptr};
-    double* d_g_dc[kPipe] = {nullptr, nullptr};
-    double* d_g_cd[kPipe] = {nullptr, nullptr};
-    double* d_lp[kPipe] = {nullptr, nullptr};
-    cudaStream_t st_h2d = nullptr, st_cmp = nullptr, st_d2h = nullptr, st_graph = nullptr;
-    cudaEvent_t ev_up[kPipe] = {nullptr, nullptr}, ev_cmp[kPipe] = {nullptr, nullptr},
-                ev_dn[kPipe] = {nullptr, nullptr};
+    static constexpr int kPipe = 4;          // groups of evaluations in flight: upload | compute | download overlap
+    int group_max = 1;                       // most evaluations per group (one copy each way per group), set with the staging
+    double* d_q_cd[kPipe] = {};
+    double* d_q_dc[kPipe] = {};
+    double* d_g_dc[kPipe] = {};
+    double* d_g_cd[kPipe] = {};
+    double* d_lp[kPipe] = {};
+    cudaStream_t st_h2d[2] = {}, st_cmp = nullptr, st_d2h[2] = {}, st_graph = nullptr;   // copies alternate between two streams per direction
+    cudaEvent_t ev_up[kPipe] = {}, ev_cmp[kPipe] = {}, ev_dn[kPipe] = {};
     // profiling
     bool profiling = false;
     std::vector<cudaEvent_t> prof_ev;   // triples: before lik, after lik, after finalize
@@ -474,9 +475,11 @@ void bgh_destroy(bgh_ctx* ctx)
         if (ctx->ev_cmp[i]) cudaEventDestroy(ctx->ev_cmp[i]);
         if (ctx->ev_dn[i]) cudaEventDestroy(ctx->ev_dn[i]);
     }
-    if (ctx->st_h2d) cudaStreamDestroy(ctx->st_h2d);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->st_h2d[i]) cudaStreamDestroy(ctx->st_h2d[i]);
+        if (ctx->st_d2h[i]) cudaStreamDestroy(ctx->st_d2h[i]);
+    }
     if (ctx->st_cmp) cudaStreamDestroy(ctx->st_cmp);
-    if (ctx->st_d2h) cudaStreamDestroy(ctx->st_d2h);
     if (ctx->st_graph) cudaStreamDestroy(ctx->st_graph);
     for (cudaEvent_t ev : ctx->prof_ev) cudaEventDestroy(ev);
     delete ctx;
@@ -679,6 +682,8 @@ static void fill_params(bgh_ctx* ctx, const double* q, double* grad, double* log
     fp->G_local = ctx->cfg.n_genes;
 }
 
+static int run_sharded(bgh_ctx* ctx, const double* q, double* logp, double* grad, void* stream);
+
 static int run_local(bgh_ctx* ctx, const double* q, double* logp, double* grad, double* payload,
                      bool finish_inline, cudaStream_t s)
 {
@@ -763,61 +768,127 @@ static int ensure_host_staging(bgh_ctx* ctx)
     if (ctx->st_cmp) return BGH_OK;
     BGH_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     const size_t n_cd = (size_t)ctx->cfg.n_chains * ctx->D, n_dc = (size_t)ctx->Cp * ctx->D;
+    // a group moves about 16 MB each way: two evaluations at 64 chains x 15k genes, more when a rank's block
+    // of q is small (sharded contexts, genome-wide model), so that a copy always outweighs the hand-off bubbles
+    const double eval_bytes = (double)(sizeof(double) * n_cd);
+    int gm = (int)(16.0e6 / eval_bytes + 0.5);
+    ctx->group_max = gm < 1 ? 1 : (gm > 16 ? 16 : gm);
     for (int i = 0; i < bgh_ctx::kPipe; ++i) {
-        BGH_CUDA(ctx, cudaMalloc(&ctx->d_q_cd[i], sizeof(double) * n_cd));
-        BGH_CUDA(ctx, cudaMalloc(&ctx->d_g_cd[i], sizeof(double) * n_cd));
-        BGH_CUDA(ctx, cudaMalloc(&ctx->d_q_dc[i], sizeof(double) * n_dc));
-        BGH_CUDA(ctx, cudaMalloc(&ctx->d_g_dc[i], sizeof(double) * n_dc));
-        BGH_CUDA(ctx, cudaMalloc(&ctx->d_lp[i], sizeof(double) * (size_t)ctx->Cp));
-        BGH_CUDA(ctx, cudaMemset(ctx->d_g_dc[i], 0, sizeof(double) * n_dc));
+        BGH_CUDA(ctx, cudaMalloc(&ctx->d_q_cd[i], sizeof(double) * n_cd * ctx->group_max));
+        BGH_CUDA(ctx, cudaMalloc(&ctx->d_g_cd[i], sizeof(double) * n_cd * ctx->group_max));
+        BGH_CUDA(ctx, cudaMalloc(&ctx->d_lp[i], sizeof(double) * (size_t)ctx->Cp * ctx->group_max));
         BGH_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_up[i], cudaEventDisableTiming));
         BGH_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_cmp[i], cudaEventDisableTiming));
         BGH_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_dn[i], cudaEventDisableTiming));
     }
-    BGH_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->st_h2d, cudaStreamNonBlocking));
+    // the device-layout buffers are touched by the compute stream only: one of each is enough
+    BGH_CUDA(ctx, cudaMalloc(&ctx->d_q_dc[0], sizeof(double) * n_dc));
+    BGH_CUDA(ctx, cudaMalloc(&ctx->d_g_dc[0], sizeof(double) * n_dc));
+    BGH_CUDA(ctx, cudaMemset(ctx->d_g_dc[0], 0, sizeof(double) * n_dc));
+    for (int i = 0; i < 2; ++i) {
+        BGH_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->st_h2d[i], cudaStreamNonBlocking));
+        BGH_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->st_d2h[i], cudaStreamNonBlocking));
+    }
     BGH_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->st_cmp, cudaStreamNonBlocking));
-    BGH_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->st_d2h, cudaStreamNonBlocking));
     return BGH_OK;
 }
 
+// Host entry (B1' with host buffers).  Stages: upload | compute | download.  A stream-ordered event wait in
+// front of a copy leaves a bubble of tens of microseconds on that stream's timeline (tools/event_probe.py:
+// 249 vs 161 us per upload+download pair), so (1) each copy direction ALTERNATES between two streams - one
+// stream's bubble hides under the other's copy - and (2) evaluations can travel in GROUPS of g (one H2D copy,
+// g x {transpose, evaluation, transpose}, one D2H copy per group).  kPipe groups are in flight.  Tools: BGH_E2E_GROUP overrides g, BGH_E2E_TRACE=1 prints the stage timeline of every group
+// (2: host enqueue time only), BGH_E2E_SKIP masks stages (bit 0 evaluation, 1 upload, 2 download, 3 transposes).
 int bgh_logp_grad_host_stream(bgh_ctx* ctx, int32_t n_evals, const double* q, double* logp, double* grad)
 {
     if (!ctx || !q || !logp || !grad || n_evals <= 0) return fail(ctx, BGH_EINVAL, "bgh_logp_grad_host_stream: bad argument");
     if (!ctx->uploaded) return fail(ctx, BGH_ESTATE, "bgh_logp_grad_host_stream: call bgh_upload first");
-    if (ctx->cfg.n_shared_rows != 0) return fail(ctx, BGH_ESTATE, "bgh_logp_grad_host_stream: single-rank contexts only");
+    // sharded contexts (peer mailboxes connected): q / grad are this rank's rows [C][3 + local genes]; every
+    // rank must make the same sequence of calls (each evaluation exchanges its payload with the peers)
+    const bool sharded = ctx->peer_world > 1;
+    if (!sharded && ctx->cfg.n_shared_rows != 0)
+        return fail(ctx, BGH_ESTATE, "bgh_logp_grad_host_stream: sharded context, call bgh_peer_connect first");
     int rc = ensure_host_staging(ctx);
     if (rc != BGH_OK) return rc;
     BGH_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
-    const int C = ctx->cfg.n_chains, D = ctx->D;
+    const int C = ctx->cfg.n_chains, D = ctx->D, Cp = ctx->Cp;
     const size_t n_cd = (size_t)C * D;
-    for (int i = 0; i < n_evals; ++i) {
-        const int b = i % bgh_ctx::kPipe;
-        // buffer reuse: upload of eval i may overwrite q_cd[b] only after compute of eval i-2 consumed it,
-        // compute may overwrite g_cd[b] only after the download of eval i-2 finished.
-        if (i >= bgh_ctx::kPipe) {
-            BGH_CUDA(ctx, cudaStreamWaitEvent(ctx->st_h2d, ctx->ev_cmp[b], 0));
+    // group size: enough groups to keep the three stages overlapped, at most group_max evaluations per group
+    int g = n_evals / (2 * bgh_ctx::kPipe);
+    if (const char* e = getenv("BGH_E2E_GROUP")) g = atoi(e);
+    g = g < 1 ? 1 : (g > ctx->group_max ? ctx->group_max : g);
+    const int n_groups = (n_evals + g - 1) / g;
+    const char* tr_env = getenv("BGH_E2E_TRACE");
+    const bool trace = tr_env && *tr_env == '1' && n_groups <= 256;
+    const char* sk_env = getenv("BGH_E2E_SKIP");
+    const int skip = sk_env ? atoi(sk_env) : 0;
+    std::vector<cudaEvent_t> tev;
+    if (trace) {
+        tev.resize((size_t)n_groups * 6);
+        for (auto& e : tev) BGH_CUDA(ctx, cudaEventCreate(&e));
+    }
+    double host_us = 0.0;
+    for (int k = 0; k < n_groups; ++k) {
+        const auto h0 = std::chrono::steady_clock::now();
+        const int b = k % bgh_ctx::kPipe;
+        cudaStream_t up = ctx->st_h2d[k & 1], dn = ctx->st_d2h[k & 1];
+        const int i0 = k * g, ng = (n_evals - i0 < g) ? n_evals - i0 : g;
+        // slot reuse: the upload of group k may overwrite q_cd[b] only after the compute of group k-kPipe has
+        // consumed it, compute may overwrite g_cd[b] / lp[b] only after the download of group k-kPipe finished
+        if (k >= bgh_ctx::kPipe) {
+            BGH_CUDA(ctx, cudaStreamWaitEvent(up, ctx->ev_cmp[b], 0));
             BGH_CUDA(ctx, cudaStreamWaitEvent(ctx->st_cmp, ctx->ev_dn[b], 0));
         }
-        BGH_CUDA(ctx, cudaMemcpyAsync(ctx->d_q_cd[b], q + (size_t)i * n_cd, sizeof(double) * n_cd,
-                                      cudaMemcpyHostToDevice, ctx->st_h2d));
-        BGH_CUDA(ctx, cudaEventRecord(ctx->ev_up[b], ctx->st_h2d));
+        if (trace) BGH_CUDA(ctx, cudaEventRecord(tev[6 * k + 0], up));
+        if (!(skip & 2))
+            BGH_CUDA(ctx, cudaMemcpyAsync(ctx->d_q_cd[b], q + (size_t)i0 * n_cd, sizeof(double) * n_cd * ng,
+                                          cudaMemcpyHostToDevice, up));
+        if (trace) BGH_CUDA(ctx, cudaEventRecord(tev[6 * k + 1], up));
+        BGH_CUDA(ctx, cudaEventRecord(ctx->ev_up[b], up));
         BGH_CUDA(ctx, cudaStreamWaitEvent(ctx->st_cmp, ctx->ev_up[b], 0));
-        BGH_CUDA(ctx, launch_transpose_in(ctx->d_q_cd[b], ctx->d_q_dc[b], C, ctx->Cp, D, ctx->st_cmp));
-        rc = run_local(ctx, ctx->d_q_dc[b], ctx->d_lp[b], ctx->d_g_dc[b], ctx->d_payload, true, ctx->st_cmp);
-        if (rc != BGH_OK) return rc;
-        BGH_CUDA(ctx, launch_transpose_out(ctx->d_g_dc[b], ctx->d_g_cd[b], C, ctx->Cp, D, ctx->st_cmp));
-        ctx->launches += 2;
+        if (trace) BGH_CUDA(ctx, cudaEventRecord(tev[6 * k + 2], ctx->st_cmp));
+        for (int j = 0; j < ng; ++j) {
+            if (!(skip & 8))
+                BGH_CUDA(ctx, launch_transpose_in(ctx->d_q_cd[b] + (size_t)j * n_cd, ctx->d_q_dc[0], C, Cp, D, ctx->st_cmp));
+            if (!(skip & 1)) {
+                rc = sharded ? run_sharded(ctx, ctx->d_q_dc[0], ctx->d_lp[b] + (size_t)j * Cp, ctx->d_g_dc[0], ctx->st_cmp)
+                             : run_local(ctx, ctx->d_q_dc[0], ctx->d_lp[b] + (size_t)j * Cp, ctx->d_g_dc[0], ctx->d_payload,
+                                         true, ctx->st_cmp);
+                if (rc != BGH_OK) return rc;
+            }
+            if (!(skip & 8))
+                BGH_CUDA(ctx, launch_transpose_out(ctx->d_g_dc[0], ctx->d_g_cd[b] + (size_t)j * n_cd, C, Cp, D, ctx->st_cmp));
+            ctx->launches += 2;
+        }
+        if (trace) BGH_CUDA(ctx, cudaEventRecord(tev[6 * k + 3], ctx->st_cmp));
         BGH_CUDA(ctx, cudaEventRecord(ctx->ev_cmp[b], ctx->st_cmp));
-        BGH_CUDA(ctx, cudaStreamWaitEvent(ctx->st_d2h, ctx->ev_cmp[b], 0));
-        BGH_CUDA(ctx, cudaMemcpyAsync(grad + (size_t)i * n_cd, ctx->d_g_cd[b], sizeof(double) * n_cd,
-                                      cudaMemcpyDeviceToHost, ctx->st_d2h));
-        BGH_CUDA(ctx, cudaMemcpyAsync(logp + (size_t)i * C, ctx->d_lp[b], sizeof(double) * (size_t)C,
-                                      cudaMemcpyDeviceToHost, ctx->st_d2h));
-        BGH_CUDA(ctx, cudaEventRecord(ctx->ev_dn[b], ctx->st_d2h));
+        BGH_CUDA(ctx, cudaStreamWaitEvent(dn, ctx->ev_cmp[b], 0));
+        if (trace) BGH_CUDA(ctx, cudaEventRecord(tev[6 * k + 4], dn));
+        if (!(skip & 4))
+            BGH_CUDA(ctx, cudaMemcpyAsync(grad + (size_t)i0 * n_cd, ctx->d_g_cd[b], sizeof(double) * n_cd * ng,
+                                          cudaMemcpyDeviceToHost, dn));
+        BGH_CUDA(ctx, cudaMemcpy2DAsync(logp + (size_t)i0 * C, sizeof(double) * C, ctx->d_lp[b], sizeof(double) * Cp,
+                                        sizeof(double) * C, (size_t)ng, cudaMemcpyDeviceToHost, dn));
+        if (trace) BGH_CUDA(ctx, cudaEventRecord(tev[6 * k + 5], dn));
+        BGH_CUDA(ctx, cudaEventRecord(ctx->ev_dn[b], dn));
+        host_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - h0).count();
     }
-    BGH_CUDA(ctx, cudaStreamSynchronize(ctx->st_d2h));
+    for (int i = 0; i < 2; ++i) BGH_CUDA(ctx, cudaStreamSynchronize(ctx->st_d2h[i]));
     BGH_CUDA(ctx, cudaStreamSynchronize(ctx->st_cmp));
-    BGH_CUDA(ctx, cudaStreamSynchronize(ctx->st_h2d));
+    for (int i = 0; i < 2; ++i) BGH_CUDA(ctx, cudaStreamSynchronize(ctx->st_h2d[i]));
+    if (tr_env && (*tr_env == '1' || *tr_env == '2'))
+        fprintf(stderr, "# %d evaluations in %d groups of %d; host enqueue time per evaluation %.1f us\n", n_evals, n_groups, g,
+                host_us / n_evals);
+    if (trace) {
+        fprintf(stderr, "# group  h2d[start end]  compute[start end]  d2h[start end]   (us since the first upload)\n");
+        for (int k = 0; k < n_groups; ++k) {
+            float t[6];
+            for (int j = 0; j < 6; ++j) cudaEventElapsedTime(&t[j], tev[0], tev[6 * k + j]);
+            fprintf(stderr, "%4d  %8.1f %8.1f  %8.1f %8.1f  %8.1f %8.1f\n", k, t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f,
+                    t[3] * 1e3f, t[4] * 1e3f, t[5] * 1e3f);
+        }
+        for (auto& e : tev) cudaEventDestroy(e);
+    }
     return BGH_OK;
 }
 
@@ -939,10 +1010,8 @@ int bgh_peer_connect(bgh_ctx* ctx, int32_t rank, int32_t world, const void* hand
     return BGH_OK;
 }
 
-int bgh_logp_grad_sharded(bgh_ctx* ctx, const double* q, double* logp, double* grad, void* stream)
+static int run_sharded(bgh_ctx* ctx, const double* q, double* logp, double* grad, void* stream)
 {
-    if (!ctx || !q || !logp || !grad) return fail(ctx, BGH_EINVAL, "bgh_logp_grad_sharded: null argument");
-    if (!ctx->uploaded) return fail(ctx, BGH_ESTATE, "bgh_logp_grad_sharded: call bgh_upload first");
     if (ctx->peer_world < 1) return fail(ctx, BGH_ESTATE, "bgh_logp_grad_sharded: call bgh_peer_connect first");
     if (!ctx->fused) return fail(ctx, BGH_ESTATE, "bgh_logp_grad_sharded: needs the cooperative kernels");
     LikParams lp;
@@ -976,6 +1045,13 @@ int bgh_logp_grad_sharded(bgh_ctx* ctx, const double* q, double* logp, double* g
     }
     ctx->launches += 1;
     return BGH_OK;
+}
+
+int bgh_logp_grad_sharded(bgh_ctx* ctx, const double* q, double* logp, double* grad, void* stream)
+{
+    if (!ctx || !q || !logp || !grad) return fail(ctx, BGH_EINVAL, "bgh_logp_grad_sharded: null argument");
+    if (!ctx->uploaded) return fail(ctx, BGH_ESTATE, "bgh_logp_grad_sharded: call bgh_upload first");
+    return run_sharded(ctx, q, logp, grad, stream);
 }
 
 int bgh_peer_status(bgh_ctx* ctx, int32_t* status)

@@ -95,6 +95,17 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+def ncu_traffic(workload, world):
+    """dram bytes (read + write) per launch of the dominant kernel from the committed ncu --set full capture of
+    this workload (profiles/ncu_traffic.json); None when no capture exists for the configuration."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            e = json.load(f).get("%s:%d" % (workload, world))
+        return float(e["dram_read_bytes"] + e["dram_write_bytes"]) if e else None
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def run_cpu_baseline(d, C, target_seconds=10.0, n_threads=0):
     """Times the C restatement of the reference CPU path (oracle/oracle_c.c) on the host cores."""
     from oracle.c_oracle import COracle, num_threads
@@ -312,7 +323,7 @@ def bench_gpu(args, wl):
         except Exception:
             dfma_peak = None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic(args.workload, world), "peak_source": peak_kind,
                     "kernel": "logp_grad_fused_kernel (likelihood pass | grid barrier | finalize, one launch)" if world == 1
                     else "logp_grad_sharded_kernel (likelihood | finalize | peer all-reduce | finish, one launch)",
                     "kernel_ms": lik_ms, "finalize_ms": fin_ms,
@@ -340,34 +351,79 @@ def bench_gpu(args, wl):
             "gpu_launches": int(launches), "clocks": clk, "wall_s_timed_region": wall,
         }
     # ---- e2e: host buffers through the C ABI (H2D + transposes + kernels + D2H every step) --------
-    if world == 1:
-        n_e2e = int(min(max(K // 10, 8), 64))
-        qh = torch.empty((n_e2e, C, D), dtype=torch.float64).pin_memory()
-        gh = torch.empty((n_e2e, C, D), dtype=torch.float64).pin_memory()
+    # N>1: every rank moves ITS rows of q / grad (3 shared + its gene block) over its own PCIe link and the
+    # payload exchange runs inside the kernel; barrier on both sides, max over ranks.
+    e2e_ok = world == 1 or args.exchange == "peer"
+    if e2e_ok:
+        Dl = eng.D
+        Ql = Q if (world == 1 or gw) else sh.local_q(Q)
+        n_e2e = int(min(max(K // 10, 8), 128))
+        qh = torch.empty((n_e2e, C, Dl), dtype=torch.float64).pin_memory()
+        gh = torch.empty((n_e2e, C, Dl), dtype=torch.float64).pin_memory()
         lh = torch.empty((n_e2e, C), dtype=torch.float64).pin_memory()
-        qh.copy_(torch.from_numpy(np.broadcast_to(Q, (n_e2e, C, D)).copy()))
-        eng.logp_grad_host_ptr(2, qh.data_ptr(), lh.data_ptr(), gh.data_ptr())   # warm-up (allocs staging)
+        qh.copy_(torch.from_numpy(np.broadcast_to(Ql, (n_e2e, C, Dl)).copy()))
+        # warm-up: the whole buffer set once (allocates the staging; the first DMA to a fresh pinned page is slow in this VM)
+        eng.logp_grad_host_ptr(n_e2e, qh.data_ptr(), lh.data_ptr(), gh.data_ptr())
         l0 = eng.launch_count
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         eng.logp_grad_host_ptr(n_e2e, qh.data_ptr(), lh.data_ptr(), gh.data_ptr())
         dt = time.perf_counter() - t0
-        line["e2e"] = {"value": n_e2e * C / dt, "unit": UNIT, "h2d_bytes_per_step": C * D * 8,
-                       "d2h_bytes_per_step": C * D * 8 + C * 8, "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3,
-                       "api": "bgh_logp_grad_host_stream (pinned host q[C][D] -> logp[C], grad[C][D]; copies, layout "
-                              "transposes and kernels of consecutive steps overlapped on 3 streams)",
-                       "gpu_launches": eng.launch_count - l0}
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
         # check the e2e result against the device path
         lp_dev = logp[:C].cpu().numpy()
         assert np.allclose(lh[-1].numpy(), lp_dev, rtol=1e-12), "e2e result differs from device path"
+        assert np.array_equal(gh[-1].numpy(), eng.from_device_layout(grad).cpu().numpy()), "e2e gradient differs from device path"
+        if rank == 0:
+            line["e2e"] = {"value": n_e2e * C / dt, "unit": UNIT, "h2d_bytes_per_step": C * Dl * 8,
+                           "d2h_bytes_per_step": C * Dl * 8 + C * 8, "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3,
+                           "api": "bgh_logp_grad_host_stream (pinned host q[C][D] -> logp[C], grad[C][D]; copies, layout "
+                                  "transposes and kernels of consecutive steps overlapped on 3 streams, 4 evaluations in flight)",
+                           "gpu_launches": eng.launch_count - l0}
+            if world > 1:
+                line["e2e"]["note"] = ("bytes are per rank: each rank copies its own rows of q/grad (3 shared + %d local genes) "
+                                       "over its own PCIe link; wall clock, barrier before, max over ranks" % (Dl - 3))
     elif rank == 0:
         line["e2e"] = None
     if rank == 0 and world == 1 and not args.no_sampler:
         line["sampler"] = run_sampler_section(eng, args, C)
+    if world > 1 and not gw:
+        # Chains are independent units: every rank evaluates its OWN C chains on the FULL dataset, no collective
+        # (weak scaling in chains: N x C chains in total).  Reported beside the sharded strong-scaling value.
+        eng.close()
+        eng = Engine(d.chi2, d.ld, d.gene_id, G, d.c, C, device=local_rank)
+        q_full = eng.to_device_layout(Q)
+        g_full = torch.zeros_like(q_full)
+        for _ in range(max(args.warmup, 3)):
+            eng.logp_grad(q_full, logp, g_full)
+        n_rep = min(K, 500)
+        r0 = [torch.cuda.Event(enable_timing=True) for _ in range(n_rep)]
+        r1 = [torch.cuda.Event(enable_timing=True) for _ in range(n_rep)]
+        torch.cuda.synchronize()
+        dist.barrier()
+        for i in range(n_rep):
+            if not args.no_flush:
+                flush.fill_(i & 0xFF)
+            r0[i].record()
+            eng.logp_grad(q_full, logp, g_full)
+            r1[i].record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in zip(r0, r1)) / n_rep], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            line["chain_replicas"] = {"value": world * C / (float(t.item()) * 1e-3), "unit": UNIT, "scaling": "weak",
+                                      "chains_total": world * C, "ms_per_step": float(t.item()), "steps": n_rep,
+                                      "note": "every GPU evaluates its own %d chains on the full dataset (no collective); "
+                                              "per-step CUDA events, L2 flushed, max over ranks" % C}
     if world > 1 and not args.no_sampler:
         # ESS/s at N GPUs: independent chain replicas (every rank runs its own C chains on the FULL dataset,
         # no collective; the gene-block sharded tick kernel is not built yet)
-        eng.close()
-        eng = Engine(d.chi2, d.ld, d.gene_id, G, d.c, C, device=local_rank)
         sm = run_sampler_section(eng, args, C, seed=1 + rank)
         vec = torch.tensor([sm["ess_min_scalar"], sm["seconds_draws"], sm["ess_median_beta"],
                             sm["chain_leapfrogs_per_sec_post_tune"]], dtype=torch.float64, device=dev)

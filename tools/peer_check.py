@@ -56,7 +56,16 @@ for name, fn in (("nccl", nccl_step), ("fused", fused_step)):
     t = torch.tensor([e0.elapsed_time(e1) / n * 1e3], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0: print("%s exchange: %.2f us/step (max over %d ranks)" % (name, float(t), world), flush=True)
 assert eng.peer_status() == 0
+# host entry on the sharded context: pinned local rows in, local gradient rows out, same bits as the device path
+n_h = 6
+qh = np.broadcast_to(sh.local_q(Q), (n_h, C, eng.D)).copy()
+lph, gh = eng.logp_grad_host(qh)
+fused_step(); torch.cuda.synchronize()
+assert np.array_equal(lph[-1], lp2[:C].cpu().numpy()) and np.array_equal(lph[0], lph[-1])
+assert np.array_equal(gh[-1], eng.from_device_layout(g2).cpu().numpy())
+assert eng.peer_status() == 0
 if rank == 0:
+    print("sharded host entry == device path", flush=True)
     print("fused vs nccl: logp rel %.2e grad rel %.2e ; logp bit-identical on all ranks: %s" % (err_lp, err_g, same), flush=True)
     assert err_lp < 1e-12 and err_g < 1e-9 and same
 eng.close()
