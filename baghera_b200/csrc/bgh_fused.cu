@@ -1042,20 +1042,32 @@ cudaError_t fused_configure()
     return cudaSuccess;
 }
 
+// BGH_PLAIN_LAUNCH=1 (experiment): ordinary launch instead of cudaLaunchCooperativeKernel.  The grid is one CTA
+// per SM, so the CTAs are co-resident as soon as the SMs are free; the grid barrier has a timeout either way.
+static bool plain_launch()
+{
+    static const bool v = [] { const char* e = getenv("BGH_PLAIN_LAUNCH"); return e && *e == '1'; }();
+    return v;
+}
+static cudaError_t launch_grid(const void* fn, int n_cta, void** args, cudaStream_t s)
+{
+    if (plain_launch()) return cudaLaunchKernel(fn, dim3(n_cta), dim3(kLikThreads), args, kLikSmemBytes, s);
+    return cudaLaunchCooperativeKernel(fn, dim3(n_cta), dim3(kLikThreads), args, kLikSmemBytes, s);
+}
+
 template <int CL, int CPL>
 static cudaError_t launch_fused_t(const FusedParams& f, int n_cta, cudaStream_t s)
 {
     void* args[] = {const_cast<FusedParams*>(&f)};
     const void* fn = f.lik.model == BGH_MODEL_GENE_GAMMA ? (const void*)logp_grad_fused_kernel<CL, CPL, true>
                                                          : (const void*)logp_grad_fused_kernel<CL, CPL, false>;
-    return cudaLaunchCooperativeKernel(fn, dim3(n_cta), dim3(kLikThreads), args, kLikSmemBytes, s);
+    return launch_grid(fn, n_cta, args, s);
 }
 template <int CL, int CPL>
 static cudaError_t launch_sharded_t(const FusedParams& f, const PeerParams& pr, int n_cta, cudaStream_t s)
 {
     void* args[] = {const_cast<FusedParams*>(&f), const_cast<PeerParams*>(&pr)};
-    return cudaLaunchCooperativeKernel((const void*)logp_grad_sharded_kernel<CL, CPL, false>, dim3(n_cta), dim3(kLikThreads), args,
-                                       kLikSmemBytes, s);     // the gamma model runs on single-rank contexts
+    return launch_grid((const void*)logp_grad_sharded_kernel<CL, CPL, false>, n_cta, args, s);   // the gamma model runs on single-rank contexts
 }
 template <int CL, int CPL>
 static cudaError_t launch_tick_t(const TickParams& t, int n_cta, cudaStream_t s)

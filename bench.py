@@ -265,30 +265,24 @@ def bench_gpu(args, wl):
     K = args.steps
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    eng.set_profiling(True)
     launches0 = eng.launch_count
     clocks = ClockSampler(local_rank).start() if rank == 0 else None
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     wall0 = time.perf_counter()
-    prof_lik, prof_fin, prof_n = 0.0, 0.0, 0
+    # a step is ONE kernel launch: the per-step events on the launch stream time exactly that launch (no
+    # other event records inside the region - each record costs a few microseconds of stream time)
     for i in range(K):
         if not args.no_flush:
             flush.fill_(i & 0xFF)
         ev0[i].record()
         step()
         ev1[i].record()
-        if (i + 1) % 2000 == 0:                    # drain the library's event ring
-            a, b, n = eng.kernel_time_ms(reset=True)
-            prof_lik += a * n; prof_fin += b * n; prof_n += n
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     wall = time.perf_counter() - wall0
-    a, b, n = eng.kernel_time_ms(reset=True)
-    prof_lik += a * n; prof_fin += b * n; prof_n += n
-    eng.set_profiling(False)
     clk = clocks.stop() if clocks else None
     launches = eng.launch_count - launches0
     step_ms = sum(e0.elapsed_time(e1) for e0, e1 in zip(ev0, ev1)) / K
@@ -312,8 +306,7 @@ def bench_gpu(args, wl):
     line = None
     if rank == 0:
         peaks, peak_kind = measured_peaks()
-        lik_ms = prof_lik / max(prof_n, 1)
-        fin_ms = prof_fin / max(prof_n, 1)
+        lik_ms = step_ms        # one launch per step (with --exchange nccl: local pass + NCCL all-reduce + finish)
         Ml, Dl = eng.M, eng.D
         b_alg = (8.0 if gw else 12.0) * Ml + 16.0 * C * Dl + 8.0 * C   # SNP stream (no gene id in the gw model) + q + grad + logp
         achieved = b_alg / (lik_ms * 1e-3) / 1e9 if lik_ms > 0 else 0.0
@@ -326,7 +319,7 @@ def bench_gpu(args, wl):
                     "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic(args.workload, world), "peak_source": peak_kind,
                     "kernel": "logp_grad_fused_kernel (likelihood pass | grid barrier | finalize, one launch)" if world == 1
                     else "logp_grad_sharded_kernel (likelihood | finalize | peer all-reduce | finish, one launch)",
-                    "kernel_ms": lik_ms, "finalize_ms": fin_ms,
+                    "kernel_ms": lik_ms,
                     "algorithmic_bytes_per_launch": b_alg,
                     "bytes_streamed_per_launch": 28.0 * Ml + 16.0 * C * Dl + 8.0 * C,
                     "note": "algorithmic bytes per SURVEY 8d (fp32 chi2/ld + int32 gene id = 12 B/SNP); the kernel streams a prepared "
