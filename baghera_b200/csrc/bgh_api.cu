@@ -310,7 +310,8 @@ struct bgh_ctx {
     unsigned char* d_mailbox = nullptr;      // [flags 2 x kMaxPeers x 128 B][mail 2 x kMaxPeers x n doubles]
     unsigned char* peer_base[kMaxPeers] = {nullptr};
     int peer_rank = -1, peer_world = 0;
-    unsigned long long peer_epoch = 0;
+    unsigned long long peer_epoch = 0;       // launches that used mailbox region A (evaluation payload)
+    unsigned long long nuts_epoch = 0;       // launches that used mailbox region B (sampler sums)
     // host-entry staging (lazily allocated)
     static constexpr int kPipe = 4;          // groups of evaluations in flight: upload | compute | download overlap
     int group_max = 1;                       // most evaluations per group (one copy each way per group), set with the staging
@@ -680,6 +681,7 @@ static void fill_params(bgh_ctx* ctx, const double* q, double* grad, double* log
     fp->fix = ctx->cfg.fix_intercept; fp->finish_inline = 0; fp->c = ctx->cfg.c; fp->lik_const = ctx->lik_const; fp->gamma_rate = ctx->cfg.gamma_rate;
     fp->first_gene_row = ctx->cfg.first_gene_row; fp->last_gene_row = ctx->cfg.last_gene_row;
     fp->G_local = ctx->cfg.n_genes;
+    fp->n_shared_rows = ctx->cfg.n_shared_rows;
 }
 
 static int run_sharded(bgh_ctx* ctx, const double* q, double* logp, double* grad, void* stream);
@@ -963,10 +965,17 @@ int bgh_dfma_peak(bgh_ctx* ctx, double* ginstr_per_s)
 // ---------------------------------------------------------------------------------------------
 // sharded evaluation with the payload all-reduce fused into the kernel (peer-mapped mailboxes)
 // ---------------------------------------------------------------------------------------------
+// Mailbox of one rank (one allocation, one IPC handle): region A = evaluation payload, region B = the sharded
+// sampler's per-chain sums; each region is [flags 2 x kMaxPeers x 128 B][mail 2 x kMaxPeers x n doubles].
 static constexpr size_t kFlagBytes = 2 * (size_t)kMaxPeers * 128;
+static size_t mailbox_a_bytes(const bgh_ctx* ctx)
+{
+    const size_t b = kFlagBytes + 2 * (size_t)kMaxPeers * (size_t)(4 + ctx->cfg.n_shared_rows) * ctx->Cp * sizeof(double);
+    return (b + 127) / 128 * 128;
+}
 static size_t mailbox_bytes(const bgh_ctx* ctx)
 {
-    return kFlagBytes + 2 * (size_t)kMaxPeers * (size_t)(4 + ctx->cfg.n_shared_rows) * ctx->Cp * sizeof(double);
+    return mailbox_a_bytes(ctx) + kFlagBytes + 2 * (size_t)kMaxPeers * (size_t)kNutsMaxPartials * ctx->Cp * sizeof(double);
 }
 
 int32_t bgh_peer_handle_bytes(void) { return (int32_t)sizeof(cudaIpcMemHandle_t); }
@@ -1007,6 +1016,7 @@ int bgh_peer_connect(bgh_ctx* ctx, int32_t rank, int32_t world, const void* hand
     ctx->peer_rank = rank;
     ctx->peer_world = world;
     ctx->peer_epoch = 0;
+    ctx->nuts_epoch = 0;
     return BGH_OK;
 }
 
@@ -1083,7 +1093,9 @@ static int nuts_params(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nuts
 {
     if (!ctx || !buf || !cfg) return fail(ctx, BGH_EINVAL, "bgh_nuts: null argument");
     if (!ctx->uploaded) return fail(ctx, BGH_ESTATE, "bgh_nuts: call bgh_upload first");
-    if (ctx->cfg.n_shared_rows != 0) return fail(ctx, BGH_ESTATE, "bgh_nuts: the device sampler runs on single-rank contexts");
+    const bool sharded = ctx->cfg.n_genes_total != ctx->cfg.n_genes || ctx->cfg.n_shared_rows != 0 || ctx->peer_world > 1;
+    if (sharded && ctx->peer_world < 2)
+        return fail(ctx, BGH_ESTATE, "bgh_nuts: sharded context, call bgh_peer_connect first");
     if (!buf->state || !buf->ckpt || !buf->sc || !buf->fl || !buf->partials || !buf->sums || !buf->logp_w ||
         !buf->n_active_dev || !buf->n_active_host)
         return fail(ctx, BGH_EINVAL, "bgh_nuts: null buffer");
@@ -1091,6 +1103,20 @@ static int nuts_params(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nuts
     p->sums = buf->sums; p->logp_w = buf->logp_w; p->n_active = buf->n_active_dev;
     p->D = ctx->D; p->Cp = ctx->Cp; p->C = ctx->cfg.n_chains; p->n_vec_blocks = 2 * ctx->sm_count;
     p->coord_offset = cfg->coord_offset; p->seed = cfg->seed; p->draw = draw;
+    p->head_rows = 0; p->own_head = 1; p->own_first = 1; p->status = ctx->d_status;
+    memset(&p->peer, 0, sizeof(p->peer));
+    if (sharded) {
+        // rows in front of the per-gene block (the whole vector in the genome-wide model) are replicated
+        p->head_rows = ctx->cfg.model == BGH_MODEL_GW_NORMAL ? ctx->D : (ctx->cfg.model == BGH_MODEL_GENE_GAMMA ? 2 : 3);
+        p->own_head = ctx->peer_rank == 0 ? 1 : 0;
+        p->own_first = ctx->cfg.first_gene_partial ? 0 : 1;
+        for (int r = 0; r < ctx->peer_world; ++r) {
+            unsigned char* const base = ctx->peer_base[r] + mailbox_a_bytes(ctx);
+            p->peer.flag[r] = reinterpret_cast<unsigned long long*>(base);
+            p->peer.mail[r] = reinterpret_cast<double*>(base + kFlagBytes);
+        }
+        p->peer.rank = ctx->peer_rank; p->peer.world = ctx->peer_world;
+    }
     p->emax = cfg->emax; p->target_accept = cfg->target_accept; p->da_gamma = cfg->da_gamma;
     p->da_kappa = cfg->da_kappa; p->da_t0 = cfg->da_t0;
     return BGH_OK;
@@ -1103,7 +1129,8 @@ int bgh_nuts_init(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nuts_cfg*
     if (rc != BGH_OK) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t vec = (size_t)ctx->D * ctx->Cp;
-    rc = run_local(ctx, buf->state + kSlotQP * vec, buf->logp_w, buf->state + kSlotGP * vec, ctx->d_payload, true, s);
+    rc = p.peer.world > 1 ? run_sharded(ctx, buf->state + kSlotQP * vec, buf->logp_w, buf->state + kSlotGP * vec, s)
+                          : run_local(ctx, buf->state + kSlotQP * vec, buf->logp_w, buf->state + kSlotGP * vec, ctx->d_payload, true, s);
     if (rc != BGH_OK) return rc;
     const int Dtot = cfg->n_dim_total > 0 ? cfg->n_dim_total : ctx->D;
     const double step0 = cfg->step_scale / pow((double)Dtot, 0.25);
@@ -1136,6 +1163,9 @@ int bgh_nuts_transition(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nut
     double* const gw = buf->state + kSlotGW * vec;
     int leapfrogs = 0;
 
+    // sharded: every scalar kernel that consumes per-chain sums all-reduces them over mailbox region B
+    auto next_epoch = [&] { if (p.peer.world > 1) p.peer.epoch = ++ctx->nuts_epoch; };
+    next_epoch();
     BGH_CUDA(ctx, nuts_launch_begin(p, s));
     ctx->launches += 2;
     for (int depth = 0; depth < max_treedepth; ++depth) {
@@ -1144,7 +1174,8 @@ int bgh_nuts_transition(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nut
         const int n_leaves = 1 << depth;
         for (int leaf = 0; leaf < n_leaves; ++leaf) {
             BGH_CUDA(ctx, nuts_launch_leap1(p, leaf == 0 ? 1 : 0, s));
-            rc = run_local(ctx, qw, buf->logp_w, gw, ctx->d_payload, true, s);
+            rc = p.peer.world > 1 ? run_sharded(ctx, qw, buf->logp_w, gw, s)
+                                  : run_local(ctx, qw, buf->logp_w, gw, ctx->d_payload, true, s);
             if (rc != BGH_OK) return rc;
             // checkpoint bookkeeping of the iterative tree (see bgh_sampler.cu)
             int idx_max = 0;
@@ -1158,10 +1189,12 @@ int bgh_nuts_transition(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nut
                 lvl_max = idx_max;
                 lvl_min = idx_max - ones + 1;
             }
+            next_epoch();
             BGH_CUDA(ctx, nuts_launch_leap2(p, leaf, store_level, lvl_min, lvl_max, s));
             ctx->launches += kNutsLaunchesPerLeaf;
             ++leapfrogs;
         }
+        next_epoch();
         BGH_CUDA(ctx, nuts_launch_end_doubling(p, max_treedepth, s));
         ctx->launches += 3;
         BGH_CUDA(ctx, cudaMemcpyAsync(buf->n_active_host, buf->n_active_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -1185,6 +1218,9 @@ int bgh_nuts_run(bgh_ctx* ctx, const bgh_nuts_async_buffers* buf, const bgh_nuts
     AsyncParams a;
     int rc = nuts_params(ctx, &buf->base, cfg, 0, &a.n);
     if (rc != BGH_OK) return rc;
+    if (a.n.peer.world > 1)
+        return fail(ctx, BGH_ESTATE, "bgh_nuts_run: the persistent tick kernel runs on single-rank contexts; "
+                                     "sharded contexts use bgh_nuts_transition");
     if (!buf->afl || (draws > 0 && !buf->trace) || tune < 0 || draws < 0 || tune + draws <= 0)
         return fail(ctx, BGH_EINVAL, "bgh_nuts_run: bad argument");
     if (ctx->Cp > 128) return fail(ctx, BGH_EINVAL, "bgh_nuts_run: at most 128 chains per context (use several contexts / GPUs)");

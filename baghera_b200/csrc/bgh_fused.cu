@@ -21,6 +21,7 @@
 #include "bgh_fused.h"
 #include "bgh_internal.h"
 #include "bgh_lik_device.cuh"
+#include "bgh_peer_device.cuh"
 #include "bgh_sampler.h"
 #include "bgh_sampler_device.cuh"
 
@@ -136,6 +137,11 @@ __device__ __forceinline__ void fin_phase(const FinParams& p, unsigned char* sme
         if (lane == 0) {
             sm[warp] = acc;
             if (on) p.payload[(size_t)which * Cp + ch] = acc;   // rows 0..3 of the payload are [4][Cp]
+            // the all-reduce leaves TOTALS in the payload: rows of rank-shared genes this rank does not hold
+            // must contribute zero to the next exchange
+            if (on && which == 0 && !p.finish_inline)
+                for (int r = 0; r < p.n_shared_rows; ++r)
+                    if (r != p.first_gene_row && r != p.last_gene_row) p.payload[(size_t)(4 + r) * Cp + ch] = 0.0;
         }
         __syncthreads();
         if (p.finish_inline && which == 0 && lane == 0 && on) {
@@ -234,59 +240,6 @@ __global__ void __launch_bounds__(kLikThreads, 1) logp_grad_fused_kernel(const F
 // double buffered by launch parity: a rank can only be one launch ahead of its slowest peer, because it
 // needs that peer's flag of launch e to finish launch e.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p)
-{
-    double v;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// executed by one whole CTA; on return payload[0..n) holds the rank-ordered total on every rank
-__device__ __forceinline__ void peer_allreduce(const PeerParams& pr, double* payload, int* status)
-{
-    const int tid = threadIdx.x;
-    const int par = (int)(pr.epoch & 1ull);
-    const size_t my_box = ((size_t)par * pr.world + pr.rank) * pr.n;
-    for (int r = 0; r < pr.world; ++r) {
-        if (r == pr.rank) continue;
-        double* const dst = pr.mail[r] + my_box;
-        for (int i = tid; i < pr.n; i += blockDim.x) dst[i] = payload[i];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < pr.world && tid != pr.rank) {
-        st_release_sys_u64(pr.flag[tid] + ((size_t)par * pr.world + pr.rank) * 16, pr.epoch);
-        const unsigned long long* const mine = pr.flag[pr.rank] + ((size_t)par * pr.world + tid) * 16;
-        const unsigned long long t0 = global_timer_ns();
-        unsigned spins = 0;
-        while (ld_acquire_sys_u64(mine) < pr.epoch) {
-            if ((++spins & 255u) == 0 && (global_timer_ns() - t0 > kBarrierTimeoutNs || ld_volatile_i32(status) != 0)) {
-                atomicExch(status, 2);
-                break;
-            }
-        }
-    }
-    __syncthreads();
-    const double* const box = pr.mail[pr.rank] + (size_t)par * pr.world * pr.n;
-    for (int i = tid; i < pr.n; i += blockDim.x) {
-        const double own = payload[i];
-        double t = 0.0;
-        for (int r = 0; r < pr.world; ++r) t += (r == pr.rank) ? own : ld_relaxed_sys_f64(box + (size_t)r * pr.n + i);
-        payload[i] = t;
-    }
-    __syncthreads();
-}
-
 template <int CL, int CPL, bool GAMMA>
 __global__ void __launch_bounds__(kLikThreads, 1) logp_grad_sharded_kernel(const FusedParams f, const PeerParams pr)
 {

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include "bgh_internal.h"
+#include "bgh_peer.h"
 #include "bgh_sampler.h"
 
 namespace bgh {
@@ -15,16 +16,6 @@ struct FusedParams {
     unsigned long long bar_base;   // value of *bar when this launch starts (tracked by the host)
     int* status;        // device flag: 0 ok, 1 = a grid barrier timed out
     int chain_blocks;   // chain blocks of CL*CPL chains, walked sequentially by every CTA
-};
-
-// one-shot all-reduce of the payload over peer-mapped memory (NVLink P2P stores + system-scope flags)
-constexpr int kMaxPeers = 8;
-struct PeerParams {
-    double* mail[kMaxPeers];                  // mail[r]: rank r's mailbox [2 parities][world][n] (mail[rank] is local)
-    unsigned long long* flag[kMaxPeers];      // flag[r]: rank r's flags  [2 parities][world] x 16 words (128-byte lines)
-    int rank, world;
-    int n;                                    // payload doubles = payload rows * Cp
-    unsigned long long epoch;                 // launch counter, >= 1, identical on every rank
 };
 
 struct TickParams {

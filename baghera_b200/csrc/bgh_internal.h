@@ -102,6 +102,7 @@ struct FinParams {
     double gamma_rate;
     // finish-only
     int first_gene_row, last_gene_row, G_local;
+    int n_shared_rows;    // payload rows 4.. : a row of a rank-shared gene this rank does NOT hold is zeroed every launch
 };
 
 // kernel launchers (bgh_lik.cu)

@@ -88,6 +88,10 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinParams p
                 for (int r = 0; r < R; ++r) tot += sm[r * nb + tid];
                 sm[tid] = tot;
                 p.payload[(tid / nc) * Cp + c0 + (tid % nc)] = tot;   // rows 0..3 of the payload are [4][Cp]
+                // rows of rank-shared genes this rank does not hold contribute zero (the all-reduce leaves totals there)
+                if (tid < nc && !p.finish_inline)
+                    for (int r = 0; r < p.n_shared_rows; ++r)
+                        if (r != p.first_gene_row && r != p.last_gene_row) p.payload[(size_t)(4 + r) * Cp + c0 + tid] = 0.0;
             }
             __syncthreads();
             if (p.finish_inline && tid < nc) {

@@ -178,12 +178,22 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
     if (p.trace != nullptr && lane == 0)
         p.trace[((size_t)(chain_block * p.n_cta + cta) * kLikWarps + warp) * 8 + 7] = sm_id();
 
-    // ---- group descriptor, then get the first copies in flight before the exp() preamble --------
+    // ---- preamble: every global load is issued before the first dependent use ------------------
+    // (cold L2: descriptor -> first beta rows is a dependent chain of two HBM round trips; the shared rows of q
+    // and the exp()/sigmoid() of the per-chain constants run underneath it)
     const int4 desc = p.groups[v];
+    const long long ds = p.ds, cs = p.cs;
+    double q0[CPL], q1[CPL], q2[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+        const int ch = ch0 + k * CL;
+        q0[k] = p.q[0 * ds + ch * cs];
+        q1[k] = p.q[1 * ds + ch * cs];
+        q2[k] = (gene_model && !gamma_model) ? p.q[2 * ds + ch * cs] : 0.0;
+    }
     const int ra = desc.x, rb = desc.y, flags = desc.z, g_first = desc.w;
     const bool exclusive = (flags & kExclusive) != 0;
     const bool active = ra < rb;
-    const long long ds = p.ds, cs = p.cs;
     const double* const beta = p.q + (long long)row0 * ds + (long long)ch0 * cs;   // per-gene rows (this lane's chains)
 
     const int base0 = ra & ~(CH - 1);   // CH aligned: every bulk copy source is 16-byte aligned
@@ -222,27 +232,19 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
     double ne[CPL], mi[CPL], iW2[CPL];   // ne = -e
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
-        const int ch = ch0 + k * CL;
         if (gamma_model) {
             // ref: gene_regression.py:229-248 — q = [e, mi_logodds__, beta_log__...]
-            const double ev = p.q[0 * ds + ch * cs];
-            const double xm = p.q[1 * ds + ch * cs];
             iW2[k] = 0.0;
-            mi[k] = sigmoid_d(xm);
-            ne[k] = p.fix ? -1.0 : -ev;              // ref: gene_regression.py:234-240
+            mi[k] = sigmoid_d(q1[k]);
+            ne[k] = p.fix ? -1.0 : -q0[k];           // ref: gene_regression.py:234-240
         } else if (gene_model) {
-            const double xW = p.q[0 * ds + ch * cs];
-            const double ev = p.q[1 * ds + ch * cs];
-            const double xm = p.q[2 * ds + ch * cs];
-            iW2[k] = exp(-2.0 * xW);
-            mi[k] = sigmoid_d(xm);
-            ne[k] = p.fix ? -1.0 : -ev;              // ref: gene_regression.py:85-90
+            iW2[k] = exp(-2.0 * q0[k]);
+            mi[k] = sigmoid_d(q2[k]);
+            ne[k] = p.fix ? -1.0 : -q1[k];           // ref: gene_regression.py:85-90
         } else {
-            const double x0 = p.q[0 * ds + ch * cs];
-            const double xm = p.q[1 * ds + ch * cs];
             iW2[k] = 0.0;
-            mi[k] = sigmoid_d(xm);
-            ne[k] = p.fix ? -(kGwFixLo + (kGwFixHi - kGwFixLo) * sigmoid_d(x0)) : -x0;
+            mi[k] = sigmoid_d(q1[k]);
+            ne[k] = p.fix ? -(kGwFixLo + (kGwFixHi - kGwFixLo) * sigmoid_d(q0[k])) : -q0[k];
             braw[k] = bn[k] = mi[k];                 // the single slope of heritability.py:50-55
         }
     }

@@ -26,6 +26,7 @@
 
 #include "bgh_internal.h"
 #include "bgh_sampler.h"
+#include "bgh_peer_device.cuh"
 #include "bgh_sampler_device.cuh"
 
 namespace bgh {
@@ -49,6 +50,16 @@ __device__ __forceinline__ VecIdx vec_index(const NutsParams& p)
     v.rstep = gridDim.x * rpb;
     v.on = v.chain < p.Cp;
     return v;
+}
+
+// sharded runs: global coordinate of local row d, and whether this rank counts row d in the per-chain sums
+__device__ __forceinline__ unsigned global_coord(const NutsParams& p, int d)
+{
+    return (unsigned)(d >= p.head_rows ? d + p.coord_offset : d);
+}
+__device__ __forceinline__ bool row_owned(const NutsParams& p, int d)
+{
+    return d < p.head_rows ? p.own_head != 0 : (d == p.head_rows ? p.own_first != 0 : true);
 }
 
 template <int NK>
@@ -100,6 +111,14 @@ __device__ void reduce_partials(const NutsParams& p, int nk)
         }
         __syncthreads();
     }
+    if (p.peer.world > 1) {
+        // every rank holds the sums over ITS rows: add the ranks' contributions in rank order (bit-identical
+        // totals everywhere, so all ranks take the same tree decisions)
+        PeerParams pr = p.peer;
+        pr.n = n_out;
+        __threadfence();
+        peer_allreduce(pr, p.sums, p.status);
+    }
 }
 __device__ __forceinline__ double sum_partials(const NutsParams& p, int k, int c) { return p.sums[(size_t)k * p.Cp + c]; }
 
@@ -125,7 +144,7 @@ __global__ void __launch_bounds__(kVecThreads) nuts_begin_kernel(const NutsParam
         for (int d = v.r0; d < p.D; d += v.rstep) {
             const size_t i = (size_t)d * p.Cp + v.chain;
             // one normal per (coordinate, chain): Box-Muller on a Philox block keyed by the GLOBAL coordinate
-            const double z = momentum_normal(key, p.draw, (unsigned)(p.coord_offset + d));
+            const double z = momentum_normal(key, p.draw, global_coord(p, d));
             const double var = VAR[i];
             const double mom = z * rsqrt(var);          // p ~ N(0, 1/var)   (quadpotential.random)
             P_L[i] = mom;
@@ -134,7 +153,7 @@ __global__ void __launch_bounds__(kVecThreads) nuts_begin_kernel(const NutsParam
             const double q = QP[i], g = GP[i];
             QL[i] = q; QR[i] = q;
             GL[i] = g; GR[i] = g;
-            acc[0] = fma(0.5 * var * mom, mom, acc[0]);
+            if (row_owned(p, d)) acc[0] = fma(0.5 * var * mom, mom, acc[0]);
         }
     }
     cta_reduce_store<1>(p, v, acc, 1);
@@ -240,7 +259,8 @@ __global__ void __launch_bounds__(kVecThreads) nuts_leap2_kernel(const NutsParam
             const double mom = fma(h, GW[i], PW[i]);
             PW[i] = mom;
             const double vel = var * mom;
-            acc[0] = fma(0.5 * vel, mom, acc[0]);
+            const bool own = row_owned(p, d);
+            if (own) acc[0] = fma(0.5 * vel, mom, acc[0]);
             const double ps = (leaf == 0) ? mom : PSR[i] + mom;
             PSR[i] = ps;
             if (store_level >= 0) {
@@ -251,8 +271,10 @@ __global__ void __launch_bounds__(kVecThreads) nuts_leap2_kernel(const NutsParam
                 const double2 ck = *ckpt2(p, lvl_min + l, d, v.chain);
                 const double pc = ck.x;
                 const double sub = ps - ck.y + pc;   // p_sum of the aligned block
-                acc[1 + 2 * l] = fma(sub, var * pc, acc[1 + 2 * l]);       // . v_left
-                acc[2 + 2 * l] = fma(sub, vel, acc[2 + 2 * l]);            // . v_right
+                if (own) {
+                    acc[1 + 2 * l] = fma(sub, var * pc, acc[1 + 2 * l]);       // . v_left
+                    acc[2 + 2 * l] = fma(sub, vel, acc[2 + 2 * l]);            // . v_right
+                }
             }
         }
     }
@@ -373,8 +395,10 @@ __global__ void __launch_bounds__(kVecThreads) nuts_end_doubling_kernel(const Nu
             const double pst = PST[i] + PSR[i];
             PST[i] = pst;
             const double var = VAR[i];
-            acc[0] = fma(pst, var * pw, acc[0]);
-            acc[1] = fma(pst, var * PO[i], acc[1]);
+            if (row_owned(p, d)) {
+                acc[0] = fma(pst, var * pw, acc[0]);
+                acc[1] = fma(pst, var * PO[i], acc[1]);
+            }
         }
     }
     cta_reduce_store<2>(p, v, acc, 2);

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "baghera_b200.h"
+#include "bgh_peer.h"
 
 namespace bgh {
 
@@ -52,7 +53,14 @@ struct NutsParams {
     int* n_active;      // device scalar
     int D, Cp, C;
     int n_vec_blocks;
-    int coord_offset;   // global index of local coordinate 0 (sharded runs)
+    // gene-block sharded runs: local rows [0, head_rows) are the shared parameters, replicated on
+    // every rank; local row d >= head_rows is global row d + coord_offset.  A replicated row enters the
+    // per-chain sums (kinetic energy, U-turn dots) on ONE rank only: the head rows on rank 0 (own_head), the
+    // first gene row on the lower rank when the gene continues from it (own_first = 0).  Single rank:
+    // head_rows = 0, coord_offset = 0, own_* = 1, peer.world <= 1.
+    int coord_offset, head_rows, own_head, own_first;
+    PeerParams peer;    // sums are all-reduced over peer memory inside the scalar kernels when peer.world > 1
+    int* status;        // device status word (peer time-out), may be NULL on a single rank
     unsigned long long seed;
     long long draw;
     double emax, target_accept, da_gamma, da_kappa, da_t0;

@@ -227,7 +227,8 @@ typedef struct bgh_nuts_cfg {
     double emax;            /* 1000: divergence threshold */
     double da_gamma, da_kappa, da_t0;   /* 0.05, 0.75, 10 */
     int32_t n_dim_total;    /* D over all ranks (step-size rule); 0 => bgh_dim(ctx) */
-    int32_t coord_offset;   /* global index of this rank's first coordinate */
+    int32_t coord_offset;   /* sharded contexts: genes in front of this rank's gene block (local per-gene row d is
+                             * global row d + coord_offset; the shared rows keep their index); 0 on a single rank */
     int32_t reserved[4];
 } bgh_nuts_cfg;
 

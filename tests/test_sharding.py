@@ -155,6 +155,14 @@ def test_emulated_ranks_on_one_gpu(world, M, G):
     for e, q, g, p in zip(engines, qs, grads, payloads):
         e.logp_grad_local(q, g, p)
     total = torch.stack(payloads).sum(dim=0)                           # what ncclAllReduce(sum) delivers
+    # an in-place all-reduce leaves the TOTALS in every rank's payload buffer; the next evaluation must not
+    # re-add them (rows of rank-shared genes a rank does not hold have to be zeroed by every launch)
+    for p in payloads:
+        p.copy_(total)
+    for e, q, g, p in zip(engines, qs, grads, payloads):
+        e.logp_grad_local(q, g, p)
+    total2 = torch.stack(payloads).sum(dim=0)
+    assert torch.equal(total, total2), "second evaluation differs: stale totals were re-added to the payload"
     const = sum(e.lik_const for e in engines)                          # one-off all-reduce at setup
     lps = []
     for e, q, g in zip(engines, qs, grads):

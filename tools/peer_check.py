@@ -62,7 +62,14 @@ qh = np.broadcast_to(sh.local_q(Q), (n_h, C, eng.D)).copy()
 lph, gh = eng.logp_grad_host(qh)
 fused_step(); torch.cuda.synchronize()
 assert np.array_equal(lph[-1], lp2[:C].cpu().numpy()) and np.array_equal(lph[0], lph[-1])
-assert np.array_equal(gh[-1], eng.from_device_layout(g2).cpu().numpy())
+gd = eng.from_device_layout(g2).cpu().numpy()
+if not np.array_equal(gh[-1], gd):
+    bad = np.argwhere(gh[-1] != gd)
+    print("rank %d: host-entry gradient differs at %d of %d entries; rows %s; first: host %r device %r; D_local %d"
+          % (rank, len(bad), gd.size, sorted(set(bad[:, 1].tolist()))[:12], gh[-1][tuple(bad[0])], gd[tuple(bad[0])], eng.D), flush=True)
+    for k in range(n_h):
+        print("   eval %d: mismatching entries %d" % (k, int((gh[k] != gd).sum())), flush=True)
+assert np.array_equal(gh[-1], gd)
 assert eng.peer_status() == 0
 if rank == 0:
     print("sharded host entry == device path", flush=True)
