@@ -385,6 +385,29 @@ def bench_gpu(args, wl):
         line["e2e"] = None
     if rank == 0 and world == 1 and not args.no_sampler:
         line["sampler"] = run_sampler_section(eng, args, C)
+    if world > 1 and not gw and args.exchange == "peer" and not args.no_sampler:
+        # the sampler on the gene-block shards (lock-step driver: every rank owns its rows of q, per-chain sums
+        # all-reduced over peer memory inside the sampler's scalar kernels; identical decisions on every rank)
+        from baghera_b200.sampler import NutsSampler
+        smp = NutsSampler(eng, seed=1, gene_lo=sh.gene_lo, n_dim_total=D)
+        smp.init(sh.local_q(synth.jittered_start(D, C, seed=2)))
+        dist.barrier()
+        n_t, n_d = 20, 10
+        t0 = time.perf_counter()
+        so = smp.sample_lockstep(n_d, n_t)
+        secs = time.perf_counter() - t0
+        t = torch.tensor([secs], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            nl = int(so["leapfrogs"].sum())
+            line["sharded_sampler"] = {"transitions": n_t + n_d, "batched_leapfrogs": nl, "seconds": float(t.item()),
+                                       "us_per_batched_leapfrog": float(t.item()) / max(nl, 1) * 1e6,
+                                       "mean_tree_accept": float(so["stats"][:, 1].mean()),
+                                       "divergences_after_first_10": int(so["stats"][10:, 3].sum()),
+                                       "note": "bgh_nuts_transition on sharded contexts: all %d chains advance in lock step, one "
+                                               "sharded evaluation + 3 in-kernel peer exchanges per leapfrog; tools/"
+                                               "sharded_sampler_check.py checks it against the single-GPU chains" % C}
+        del smp
     if world > 1 and not gw:
         # Chains are independent units: every rank evaluates its OWN C chains on the FULL dataset, no collective
         # (weak scaling in chains: N x C chains in total).  Reported beside the sharded strong-scaling value.
