@@ -140,9 +140,11 @@ int bgh_peer_status(bgh_ctx* ctx, int32_t* status);
  * or pinned (pinned is faster). */
 int bgh_logp_grad_host(bgh_ctx* ctx, const double* q, double* logp, double* grad);
 
-/* Pipelined host form used for throughput measurement: evaluates `n_evals` parameter batches
- * q[n][C][D] -> logp[n][C], grad[n][C][D] with H2D / compute / D2H of consecutive batches
- * overlapped on three streams.  Synchronous on return. */
+/* Pipelined host form: evaluates `n_evals` parameter batches q[n][C][D] -> logp[n][C], grad[n][C][D]
+ * with upload / compute / download of consecutive batches overlapped (copies alternate between two
+ * streams per direction, batches travel in groups of about 16 MB per copy, four groups in flight).
+ * Synchronous on return.  Sharded contexts (after bgh_peer_connect): q / grad are this rank's rows
+ * [C][3 + local genes]; every rank must make the same calls with the same n_evals. */
 int bgh_logp_grad_host_stream(bgh_ctx* ctx, int32_t n_evals, const double* q, double* logp, double* grad);
 
 /* Layout helpers on the device: chain-major [C][D] <-> gene-major [D][Cp]. */
@@ -245,7 +247,11 @@ int bgh_nuts_init(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nuts_cfg*
  * switch_window != 0 swaps the estimators (quadpotential.QuadPotentialDiagAdapt.update, driven by
  * the host because the schedule is identical for all chains).  Synchronises the stream once per
  * tree doubling (to learn whether any chain is still growing its tree).  *n_leapfrogs receives the
- * number of batched logp+grad evaluations. */
+ * number of batched logp+grad evaluations.
+ * Sharded contexts (after bgh_peer_connect; every rank calls with the same arguments, cfg->coord_offset =
+ * genes in front of the rank's block, cfg->n_dim_total = global D): every rank advances its rows of q; the
+ * per-chain sums (kinetic energy, U-turn dots) are all-reduced over peer memory inside the scalar kernels
+ * in rank order, so all ranks take bit-identical decisions and reproduce the single-rank chains. */
 int bgh_nuts_transition(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nuts_cfg* cfg, int64_t draw,
                         int32_t tune, int32_t max_treedepth, double fg_weight, double bg_weight,
                         int32_t switch_window, void* stream, int32_t* n_leapfrogs);
