@@ -296,6 +296,27 @@ int bgh_debug_trace(bgh_ctx* ctx, int32_t enable, uint64_t* out, int64_t n_words
  * G DFMA-lane-instructions / s, the compute roof of the likelihood kernel at large C. */
 int bgh_dfma_peak(bgh_ctx* ctx, double* ginstr_per_s);
 
+/* ------------------------------------------------------------------------------------------
+ * Native reader of the annotated SNP table (host only; replaces the pd.read_csv of snps.py:32-64 for
+ * the schema of docs/createdata.rst:45-47: chr, rs_id, position, cm, maf, l, gene, sample_size, z).
+ * The file is memory-mapped and parsed by n_threads threads (0 = all cores) into typed columns:
+ * kind 0 = float64 (NaN for pandas' NA spellings), kind 1 = dictionary-encoded labels ("gene", "chr";
+ * code -1 = missing; the dictionary is SORTED, so a gene code is the `cat` index of
+ * gene_regression.py:61-71), kind 2 = skipped ("rs_id").  sep is the separator character.
+ * Errors: BGH_EINVAL (unreadable file, ragged row, unparsable number) with bgh_ingest_last_error(). */
+typedef struct bgh_table bgh_table;
+int bgh_csv_read(const char* path, int32_t sep, int32_t n_threads, bgh_table** out);
+const char* bgh_ingest_last_error(void);
+int64_t bgh_table_rows(const bgh_table* t);
+int32_t bgh_table_n_columns(const bgh_table* t);
+const char* bgh_table_column_name(const bgh_table* t, int32_t column);
+int32_t bgh_table_column_kind(const bgh_table* t, int32_t column);
+const double* bgh_table_f64(const bgh_table* t, int32_t column);
+const int32_t* bgh_table_codes(const bgh_table* t, int32_t column);
+int32_t bgh_table_n_labels(const bgh_table* t, int32_t column);
+const char* bgh_table_label(const bgh_table* t, int32_t column, int32_t i);
+void bgh_table_free(bgh_table* t);
+
 #ifdef __cplusplus
 }
 #endif
