@@ -22,6 +22,16 @@ class Shard:
     cfg: dict                 # bgh_cfg sharding fields
     shared_genes: list        # global ids of the rank-shared genes (payload row k <-> shared_genes[k])
 
+    def owned_rows(self, rank, head_rows=3):
+        """Mask over this rank's local rows of q: True where the rank counts the row in the sampler's per-chain
+        sums (kinetic energy, U-turn dots).  The rule of nuts_params() in csrc/bgh_api.cu: the shared head rows
+        belong to rank 0, a gene that continues from the previous rank belongs to the LOWEST rank holding it."""
+        own = np.ones(head_rows + self.n_genes, dtype=bool)
+        own[:head_rows] = rank == 0
+        if self.cfg["first_gene_partial"]:
+            own[head_rows] = False
+        return own
+
     def local_q(self, Q):
         """Global chain-major Q[C, 3 + G] -> this rank's Q[C, 3 + n_genes]."""
         return np.concatenate([Q[:, :3], Q[:, 3 + self.gene_lo: 3 + self.gene_lo + self.n_genes]], axis=1)

@@ -88,6 +88,20 @@ def test_shard_plan(world):
         assert d.G - 1 in shards[-1].shared_genes
 
 
+@pytest.mark.parametrize("world", [2, 3, 5, 8])
+def test_every_global_row_is_owned_once(world):
+    """Sharded sampler: the per-chain sums are all-reduced over ranks, so every global coordinate must be
+    counted by exactly one rank (replicated head rows and rank-spanning genes included)."""
+    d = synth.make_arrays(20_000, 200)
+    shards = [shard_dataset(d.chi2, d.ld, d.gene_id, d.G, r, world) for r in range(world)]
+    count = np.zeros(3 + d.G, dtype=int)
+    for r, sh in enumerate(shards):
+        own = sh.owned_rows(r)
+        count[:3] += own[:3]
+        count[3 + sh.gene_lo: 3 + sh.gene_lo + sh.n_genes] += own[3:]
+    assert np.all(count == 1), np.flatnonzero(count != 1)
+
+
 def _gloo_worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
