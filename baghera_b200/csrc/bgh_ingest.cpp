@@ -154,11 +154,28 @@ int bgh_csv_read(const char* path, int32_t sep_char, int32_t n_threads, bgh_tabl
     auto* T = new (std::nothrow) bgh_table;
     if (!T) { munmap((void*)data, size); return BGH_ENOMEM; }
     T->names.resize(ncol); T->kind.assign(ncol, 0); T->f64.resize(ncol); T->codes.resize(ncol); T->dict.resize(ncol);
+    // first data line: columns outside the schema are typed by what their first value looks like
+    std::vector<Field> first(ncol);
+    int n_first = 0;
+    {
+        const char* p = body;
+        while (p < end && (*p == '\n' || *p == '\r')) ++p;
+        const char* q = p < end ? (const char*)memchr(p, '\n', (size_t)(end - p)) : nullptr;
+        const char* le = q ? q : end;
+        if (le > p && le[-1] == '\r') --le;
+        if (le > p) n_first = split_line(p, le, sep, first.data(), ncol);
+    }
     for (int c = 0; c < ncol; ++c) {
         T->names[c].assign(hf[c].b, hf[c].e);
+        const std::string& nm = T->names[c];
         // label columns of the schema; identifiers nobody reads downstream are skipped
-        if (T->names[c] == "gene" || T->names[c] == "chr") T->kind[c] = 1;
-        else if (T->names[c] == "rs_id") T->kind[c] = 2;
+        if (nm == "gene" || nm == "chr") T->kind[c] = 1;
+        else if (nm == "rs_id") T->kind[c] = 2;
+        else if (nm == "position" || nm == "cm" || nm == "maf" || nm == "l" || nm == "sample_size" || nm == "z") T->kind[c] = 0;
+        else if (n_first == ncol) {
+            double v;
+            T->kind[c] = parse_f64(std::string_view(first[c].b, (size_t)(first[c].e - first[c].b)), &v) ? 0 : 1;
+        }
     }
 
     // ---- cut the body into line-aligned byte ranges ------------------------------------------------

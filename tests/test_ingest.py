@@ -73,6 +73,10 @@ def test_edge_cases(tmp_path, built_lib):
     m = ingest.model_inputs(str(p))
     assert m["genes"] == ["GA", "NonCoding"] and m["gene_id"].tolist() == [1, 0] and m["ld"][0] == 1.0
     assert len(ingest.model_inputs(str(p), fix_mhc=True)["chi2"]) == 1
+    extra = tmp_path / "x.csv"                                           # columns outside the schema: typed by their first value
+    extra.write_text(",chr,maf,l,gene,sample_size,z,allele,score\n0,1,0.2,1.0,A,10,2,T,0.5\n1,2,0.3,2.0,B,10,3,C,NA\n")
+    x = ingest.read_snp_table(str(extra))
+    assert x["allele"].tolist() == ["T", "C"] and x["score"][0] == 0.5 and np.isnan(x["score"][1]) and x[""].tolist() == [0.0, 1.0]
     tab = tmp_path / "t.tsv"
     tab.write_text("chr\tmaf\tl\tgene\tsample_size\tz\n1\t0.2\t1.0\tA\t10\t2\n")
     assert ingest.read_snp_table(str(tab), separator="t")["z"].tolist() == [2.0]
