@@ -26,6 +26,9 @@ def _common(p, with_snp_thr):
     p.add_argument("-m", "--model", default="normal", help="regression model, one between normal/gamma")
     p.add_argument("-f", "--fix-intercept", action="store_true", default=False)
     p.add_argument("--device", type=int, default=0, help="CUDA device ordinal")
+    p.add_argument("--devices", default=None,
+                   help="comma-separated CUDA ordinals: the chains run as independent replicas over these GPUs "
+                        "(gene-heritability -m normal); default: --device only")
     p.add_argument("--seed", type=int, default=20211, help="Philox seed (the reference is unseeded)")
     p.add_argument("--trace-dtype", default="float64", choices=["float64", "float32"])
 
@@ -61,7 +64,8 @@ def main(argv=None):
         print("%s is offline data preparation (ref: baghera_tool/preprocess.py) and is out of scope of baghera_b200; "
               "run it with the reference tool." % a.command, file=sys.stderr)
         return 2
-    gr.OPTIONS.update(device=a.device, seed=a.seed, trace_dtype=a.trace_dtype)
+    devices = [int(x) for x in a.devices.split(",")] if a.devices else None
+    gr.OPTIONS.update(device=devices[0] if devices else a.device, seed=a.seed, trace_dtype=a.trace_dtype, devices=devices)
     chrom = a.chromosome if a.chromosome == "all" else a.chromosome
     if a.command == "gene-heritability":
         cmd.gene_heritability(a.input_snp_filename, a.output_genes_filename, a.output_summary_filename, a.logger_filename,

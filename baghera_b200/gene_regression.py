@@ -15,7 +15,9 @@ import pandas as pd
 from . import stats as st
 
 # run-time options that have no slot in the reference signature (set by command / cli)
-OPTIONS = dict(device=0, seed=20211, trace_dtype="float64", progress=None)
+# ``devices``: list of CUDA ordinals -> the chains run as independent replicas over these GPUs (replicas.py);
+# None = the single ``device``
+OPTIONS = dict(device=0, seed=20211, trace_dtype="float64", progress=None, devices=None)
 
 
 def build_gene_index(snp_dataset):
@@ -88,13 +90,20 @@ def analyse_normal(snps_object, output_summary_filename, output_logger, SWEEPS, 
     logging.info("Average stats: %f" % np.mean(snps_object.table["stats"].values))
 
     c = float(n_patients) / float(N_1kG)
-    eng = Engine(snp_dataset["stats"].values.astype(np.float32), snp_dataset["l"].values.astype(np.float32),
-                 cat.astype(np.int32), G, c, int(CHAINS), model="gene", fix_intercept=bool(fix_intercept),
-                 device=OPTIONS["device"])
-    sampler = NutsSampler(eng, seed=OPTIONS["seed"], target_accept=0.90)      # nuts_kwargs=dict(target_accept=0.90)
-    sampler.init(synth.jittered_start(eng.D, int(CHAINS), seed=OPTIONS["seed"] + 1, model="gene"))
+    from .replicas import sample_on_devices
+    chi2 = snp_dataset["stats"].values.astype(np.float32)
+    ld = snp_dataset["l"].values.astype(np.float32)
+    cat32 = cat.astype(np.int32)
+
+    def make_engine(device, n_chains):
+        return Engine(chi2, ld, cat32, G, c, int(n_chains), model="gene", fix_intercept=bool(fix_intercept), device=device)
+
+    devices = OPTIONS["devices"] or [OPTIONS["device"]]
     dt = torch.float32 if OPTIONS["trace_dtype"] == "float32" else torch.float64
-    out = sampler.sample(int(SWEEPS), int(TUNE), trace_dtype=dt, progress=OPTIONS["progress"])
+    start = synth.jittered_start(G + 3, int(CHAINS), seed=OPTIONS["seed"] + 1, model="gene")
+    # nuts_kwargs=dict(target_accept=0.90)
+    out, n_launches = sample_on_devices(make_engine, start, int(SWEEPS), int(TUNE), devices, OPTIONS["seed"],
+                                        trace_dtype=dt, progress=OPTIONS["progress"], target_accept=0.90)
     trace = out["trace"]                                           # [draws, D, C], unconstrained space
     n_div = int(out["stats"][int(TUNE):, 3].sum())
     if n_div:
@@ -128,8 +137,8 @@ def analyse_normal(snps_object, output_summary_filename, output_logger, SWEEPS, 
     df["mi_mean"] = mi_mean
     df["mi_median"] = mi_median
     analyse_normal.last_run = dict(seconds_tune=out["seconds_tune"], seconds_draws=out["seconds_draws"],
-                                   leapfrogs=out["leapfrogs"], stats=out["stats"], kernel_launches=eng.launch_count)
-    eng.close()
+                                   leapfrogs=out["leapfrogs"], stats=out["stats"], kernel_launches=n_launches,
+                                   devices=out["devices"])
     logging.info("analysis done")
     return df
 
