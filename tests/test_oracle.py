@@ -111,3 +111,41 @@ def test_gamma_model_forms_agree():
         h = 1e-6 if idx != 0 else 1e-7
         fd = (f(q + h * np.eye(G + 2)[idx]) - f(q - h * np.eye(G + 2)[idx])) / (2 * h)
         assert abs(fd - g_b[idx]) <= 2e-5 * max(abs(g_b[idx]), 1.0), (idx, fd, g_b[idx])
+
+
+def test_density_against_scipy_distributions(cfg1):
+    """Independent third-party pin of the density formulas: the prior / likelihood terms evaluated with
+    scipy.stats' own implementations of the distributions the reference names (InverseGamma(1,1), Normal(1,1),
+    Beta(1,1), Normal(mi, W), Normal(mu_j, sqrt(l_j)); ref: gene_regression.py:78-98) plus the change-of-variables
+    terms of the log / logodds transforms must reproduce the oracle's logp (PyMC3 itself cannot run here)."""
+    from scipy import stats
+    from scipy.special import expit
+    chi2, ld, cat = _inputs(cfg1)
+    for q in synth.jittered_start(cfg1.G + 3, 3, seed=21):
+        xW, e, xm, beta = q[0], q[1], q[2], q[3:]
+        W, mi = np.exp(xW), expit(xm)
+        lp = stats.invgamma.logpdf(W, a=1.0, scale=1.0) + xW                       # log transform: |dW/dx| = W
+        lp += stats.norm.logpdf(e, loc=1.0, scale=1.0)
+        lp += stats.beta.logpdf(mi, 1.0, 1.0) + np.log(mi) + np.log1p(-mi)          # logodds: |dmi/dx| = mi (1 - mi)
+        lp += stats.norm.logpdf(beta, loc=mi, scale=W).sum()
+        lp += stats.norm.logpdf(chi2, loc=cfg1.c * beta[cat] * ld + e, scale=np.sqrt(ld)).sum()
+        lp_b, _ = mo.logp_grad_closed(q, chi2, ld, cat, cfg1.c)
+        assert abs(lp - lp_b) <= 1e-12 * abs(lp_b)
+    # genome-wide model (ref: heritability.py:44-55): e ~ Normal(1,1), mi ~ Beta(1,2)
+    for q in synth.jittered_start(2, 3, seed=22, model="gw"):
+        e, xm = q
+        mi = expit(xm)
+        lp = stats.norm.logpdf(e, 1.0, 1.0) + stats.beta.logpdf(mi, 1.0, 2.0) + np.log(mi) + np.log1p(-mi)
+        lp += stats.norm.logpdf(chi2, loc=cfg1.c * mi * ld + e, scale=np.sqrt(ld)).sum()
+        lp_b, _ = mo.gw_logp_grad_closed(q, chi2, ld, cfg1.c)
+        assert abs(lp - lp_b) <= 1e-12 * abs(lp_b)
+    # gamma model (ref: gene_regression.py:229-247): e ~ Normal(1, 0.001), beta ~ Gamma(alpha=mi, beta=N_1kG) on exp(x)
+    n_pat, rate = 361194.0, 1290028.0
+    for q in synth.jittered_start(cfg1.G + 2, 2, seed=23, model="gamma"):
+        e, xm, blog = q[0], q[1], q[2:]
+        mi, b = expit(xm), np.exp(blog)
+        lp = stats.norm.logpdf(e, 1.0, 0.001) + stats.beta.logpdf(mi, 1.0, 1.0) + np.log(mi) + np.log1p(-mi)
+        lp += (stats.gamma.logpdf(b, a=mi, scale=1.0 / rate) + blog).sum()
+        lp += stats.norm.logpdf(chi2, loc=n_pat * b[cat] * ld + e, scale=np.sqrt(ld)).sum()
+        lp_b, _ = mo.gamma_logp_grad_closed(q, chi2, ld, cat, n_pat, rate)
+        assert abs(lp - lp_b) <= 1e-11 * abs(lp_b)
