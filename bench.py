@@ -37,7 +37,9 @@ def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)), "measured"
+            d = json.load(open(p))
+            if float(d.get("hbm_gbs", 0)) > 0:
+                return d, "measured"
         except Exception:
             pass
     return {"hbm_gbs": 6650.0}, "fallback"
