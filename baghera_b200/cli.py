@@ -28,7 +28,7 @@ def _common(p, with_snp_thr):
     p.add_argument("--device", type=int, default=0, help="CUDA device ordinal")
     p.add_argument("--devices", default=None,
                    help="comma-separated CUDA ordinals: the chains run as independent replicas over these GPUs "
-                        "(gene-heritability -m normal); default: --device only")
+                        "(one host thread, engine and sampler kernel per device); default: --device only")
     p.add_argument("--seed", type=int, default=20211, help="Philox seed (the reference is unseeded)")
     p.add_argument("--trace-dtype", default="float64", choices=["float64", "float32"])
 

@@ -79,7 +79,6 @@ def analyse_normal(snps_object, output_summary_filename, output_logger, SWEEPS, 
 
     from . import synth
     from .engine import Engine
-    from .sampler import NutsSampler
 
     snp_dataset = snps_object.table.copy().reset_index(drop=True)
     n_patients = snps_object.n_patients
@@ -156,7 +155,6 @@ def analyse_gamma(snps_object, output_summary_filename, output_logger, SWEEPS, T
 
     from . import synth
     from .engine import Engine
-    from .sampler import NutsSampler
 
     snp_dataset = snps_object.table.copy().reset_index(drop=True)
     n_patients = snps_object.n_patients
@@ -166,15 +164,20 @@ def analyse_gamma(snps_object, output_summary_filename, output_logger, SWEEPS, T
     logging.info("Model Evaluation Started")
     logging.info("Average stats: %f" % np.mean(snps_object.table["stats"].values))
 
-    eng = Engine(snp_dataset["stats"].values.astype(np.float32), snp_dataset["l"].values.astype(np.float32),
-                 cat.astype(np.int32), G, float(n_patients), int(CHAINS), model="gamma", fix_intercept=bool(fix_intercept),
-                 device=OPTIONS["device"], gamma_rate=float(N_1kG))
-    sampler = NutsSampler(eng, seed=OPTIONS["seed"], target_accept=0.90)
-    start = synth.jittered_start(eng.D, int(CHAINS), seed=OPTIONS["seed"] + 1, model="gamma")
+    from .replicas import sample_on_devices
+    chi2 = snp_dataset["stats"].values.astype(np.float32)
+    ld = snp_dataset["l"].values.astype(np.float32)
+    cat32 = cat.astype(np.int32)
+
+    def make_engine(device, n_chains):
+        return Engine(chi2, ld, cat32, G, float(n_patients), int(n_chains), model="gamma", fix_intercept=bool(fix_intercept),
+                      device=device, gamma_rate=float(N_1kG))
+
+    start = synth.jittered_start(G + 2, int(CHAINS), seed=OPTIONS["seed"] + 1, model="gamma")
     start[:, 2:] += np.log(1290028.0 / float(N_1kG))      # test value of Gamma(mi, N_1kG) = 0.5 / N_1kG
-    sampler.init(start)
     dt = torch.float32 if OPTIONS["trace_dtype"] == "float32" else torch.float64
-    out = sampler.sample(int(SWEEPS), int(TUNE), trace_dtype=dt, progress=OPTIONS["progress"])
+    out, n_launches = sample_on_devices(make_engine, start, int(SWEEPS), int(TUNE), OPTIONS["devices"] or [OPTIONS["device"]],
+                                        OPTIONS["seed"], trace_dtype=dt, progress=OPTIONS["progress"], target_accept=0.90)
     trace = out["trace"]                                           # [draws, D, C], unconstrained space
     n_div = int(out["stats"][int(TUNE):, 3].sum())
     if n_div:
@@ -227,7 +230,7 @@ def analyse_gamma(snps_object, output_summary_filename, output_logger, SWEEPS, T
     df["mi_mean"] = mi_mean
     df["mi_median"] = mi_median
     analyse_gamma.last_run = dict(seconds_tune=out["seconds_tune"], seconds_draws=out["seconds_draws"],
-                                  leapfrogs=out["leapfrogs"], stats=out["stats"], kernel_launches=eng.launch_count)
-    eng.close()
+                                  leapfrogs=out["leapfrogs"], stats=out["stats"], kernel_launches=n_launches,
+                                  devices=out["devices"])
     logging.info("analysis done")
     return df

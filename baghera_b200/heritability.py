@@ -15,21 +15,24 @@ def gw_normal(snps_object, output_summary_filename, output_logger, SWEEPS, TUNE,
 
     from . import synth
     from .engine import Engine
-    from .sampler import NutsSampler
 
     logging.info("Bayesian analysis started")
     snps_object.table = snps_object.table.reset_index(drop=True)
     nPATIENTS = snps_object.table["sample_size"][0]                       # (:42)
     c = float(nPATIENTS) / float(N_1kG)
     tab = snps_object.table
-    eng = Engine(tab["stats"].values.astype(np.float32), tab["l"].values.astype(np.float32), None, 1, c, int(CHAINS),
-                 model="gw", fix_intercept=bool(fix_intercept), device=OPTIONS["device"])
-    sampler = NutsSampler(eng, seed=OPTIONS["seed"], target_accept=0.90)
+    from .replicas import sample_on_devices
+    chi2 = tab["stats"].values.astype(np.float32)
+    ld = tab["l"].values.astype(np.float32)
+
+    def make_engine(device, n_chains):
+        return Engine(chi2, ld, None, 1, c, int(n_chains), model="gw", fix_intercept=bool(fix_intercept), device=device)
+
     start = synth.jittered_start(2, int(CHAINS), seed=OPTIONS["seed"] + 1, model="gw")
     if fix_intercept:
         start[:, 0] -= 1.0        # interval-transformed Uniform: test point = midpoint -> 0 in the unconstrained space
-    sampler.init(start)
-    out = sampler.sample(int(SWEEPS), int(TUNE), progress=OPTIONS["progress"])
+    out, n_launches = sample_on_devices(make_engine, start, int(SWEEPS), int(TUNE), OPTIONS["devices"] or [OPTIONS["device"]],
+                                        OPTIONS["seed"], progress=OPTIONS["progress"], target_accept=0.90)
     trace = out["trace"]
     x0 = trace[:, 0, :].double()
     if fix_intercept:
@@ -56,6 +59,6 @@ def gw_normal(snps_object, output_summary_filename, output_logger, SWEEPS, TUNE,
     output_logger.info(" heritability 5perc: " + str(np.percentile(tmi, 5)) + "\n")
     intercept = np.mean(te)
     gw_normal.last_run = dict(seconds_tune=out["seconds_tune"], seconds_draws=out["seconds_draws"],
-                              leapfrogs=out["leapfrogs"], stats=out["stats"])
-    eng.close()
+                              leapfrogs=out["leapfrogs"], stats=out["stats"], kernel_launches=n_launches,
+                              devices=out["devices"])
     return [intercept, mi_mean]
