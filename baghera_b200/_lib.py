@@ -41,9 +41,10 @@ class bgh_cfg(ctypes.Structure):
         ("last_gene_row", ctypes.c_int32),
         ("n_shared_rows", ctypes.c_int32),
         ("sm_count_override", ctypes.c_int32),
-        ("reserved0", ctypes.c_int32),
+        ("n_replicated", ctypes.c_int32),
         ("gamma_rate", ctypes.c_double),
-        ("reserved", ctypes.c_int32 * 2),
+        ("owns_replicated", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
     ]
 
 
@@ -69,10 +70,11 @@ class bgh_nuts_cfg(ctypes.Structure):
 
 class bgh_nuts_async_buffers(ctypes.Structure):
     _fields_ = [("base", bgh_nuts_buffers), ("afl", ctypes.c_void_p), ("trace", ctypes.c_void_p),
-                ("run_stats", ctypes.c_void_p), ("trace_f32", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("run_stats", ctypes.c_void_p), ("trace_f32", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("k6", ctypes.c_void_p)]
 
 
-NUTS_ASYNC_N_FL, NUTS_ASYNC_N_SC, NUTS_ASYNC_PARTIALS = 24, 24, 24
+NUTS_ASYNC_N_FL, NUTS_ASYNC_N_SC, NUTS_ASYNC_PARTIALS = 26, 24, 24
 NUTS_MAX_DEPTH, NUTS_N_SLOTS, NUTS_N_SC, NUTS_N_FL, NUTS_N_STATS = 10, 21, 16, 11, 8
 NUTS_MAX_PARTIALS = 1 + 2 * NUTS_MAX_DEPTH
 NUTS_SLOT_Q, NUTS_SLOT_GRAD, NUTS_SLOT_VAR = 0, 1, 2
@@ -106,6 +108,8 @@ SIGNATURES = {
     "bgh_peer_connect": (_i32, [_vp, _i32, _i32, _vp]),
     "bgh_logp_grad_sharded": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "bgh_peer_status": (_i32, [_vp, _pi32]),
+    "bgh_peer_connect_local": (_i32, [_vp, _i32, _i32, ctypes.POINTER(_vp)]),
+    "bgh_debug_peer_mode": (_i32, [_vp, _i32, _i32]),
     "bgh_logp_grad_host": (_i32, [_vp, _vp, _vp, _vp]),
     "bgh_logp_grad_host_stream": (_i32, [_vp, _i32, _vp, _vp, _vp]),
     "bgh_to_device_layout": (_i32, [_vp, _vp, _vp, _vp]),
@@ -122,6 +126,7 @@ SIGNATURES = {
     "bgh_nuts_init": (_i32, [_vp, ctypes.POINTER(bgh_nuts_buffers), ctypes.POINTER(bgh_nuts_cfg), _vp]),
     "bgh_nuts_transition": (_i32, [_vp, ctypes.POINTER(bgh_nuts_buffers), ctypes.POINTER(bgh_nuts_cfg), _i64, _i32, _i32,
                                    _dbl, _dbl, _i32, _vp, _pi32]),
+    "bgh_set_row_coords": (_i32, [_vp, _pi32]),
     "bgh_nuts_stop_tuning": (_i32, [_vp, ctypes.POINTER(bgh_nuts_buffers), ctypes.POINTER(bgh_nuts_cfg), _vp]),
     "bgh_nuts_run": (_i32, [_vp, ctypes.POINTER(bgh_nuts_async_buffers), ctypes.POINTER(bgh_nuts_cfg), _i32, _i32, _i32,
                             _vp, _pi64]),

@@ -14,15 +14,23 @@
 #include "bgh_fused.h"
 #include "bgh_internal.h"
 #include "bgh_sampler.h"
+#include "bgh_tick2.h"
 
 namespace bgh {
 
 // ---------------------------------------------------------------------------------------------
 // work planning (pure host code)
 // ---------------------------------------------------------------------------------------------
+// BGH_PLAN_SNAP overrides (tuning only): fraction of a range's length within which a cut snaps to a gene boundary
+static double plan_snap()
+{
+    static const double v = [] { const char* e = getenv("BGH_PLAN_SNAP"); return (e && *e) ? atof(e) : 0.0625; }();
+    return v;
+}
+
 int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_cta, int groups_per_cta,
                bool first_partial, bool last_partial, int first_row, int last_row, double kappa,
-               Plan* plan, std::string* err, int align)
+               Plan* plan, std::string* err, int align, int n_replicated, bool owns_replicated, double snap)
 {
     const int n_groups = n_cta * groups_per_cta;
     if (M < 0 || M > 0x7fffff00LL || n_cta <= 0 || groups_per_cta <= 0 || G <= 0) {
@@ -72,7 +80,8 @@ int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_cta, int groups_p
         int32_t run_g = 0;
         for (int32_t g = 0; g < G; ++g) {
             const int64_t sz = goff[(size_t)g + 1] - goff[g];
-            if (n_cta > 1 && (double)sz >= 1.5 * per_cta && sz >= 4 * (int64_t)groups_per_cta) {
+            // a replicated gene (sharded runs) always gets CTAs of its own: its sum then travels through a CTA slot into the payload
+            if (g < n_replicated || (n_cta > 1 && (double)sz >= 1.5 * per_cta && sz >= 4 * (int64_t)groups_per_cta)) {
                 if (goff[g] > run_start) regions.push_back({run_start, goff[g], -1, 0, run_g, g, 0.0});
                 regions.push_back({goff[g], goff[(size_t)g + 1], g, 0, g, g + 1, 0.0});
                 run_start = goff[(size_t)g + 1];
@@ -81,6 +90,10 @@ int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_cta, int groups_p
         }
         if (M > run_start || regions.empty()) regions.push_back({run_start, M, -1, 0, run_g, G, 0.0});
         if ((int)regions.size() > n_cta) {   // degenerate (tiny n_cta): one mixed region
+            if (n_replicated > 0) {
+                *err = "build_plan: more replicated genes than CTAs";
+                return BGH_EINVAL;
+            }
             regions.clear();
             regions.push_back({0, M, -1, 0, 0, G, 0.0});
         }
@@ -136,7 +149,7 @@ int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_cta, int groups_p
         const double len = (double)(r.b - r.a) / (double)ng;
         if (r.gene >= 0) {
             // exclusive CTAs: equal cuts, every group flagged kExclusive; one slot per CTA
-            const bool owned_here = !(r.gene == 0 && first_partial);
+            const bool owned_here = !(r.gene == 0 && first_partial) && !(r.gene < n_replicated && !owns_replicated);
             for (int k = 0; k < ng; ++k) {
                 const int64_t x = r.a + (int64_t)llround((double)k * len);
                 P.off[(size_t)(v0 + k)] = (int32_t)x;
@@ -153,9 +166,10 @@ int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_cta, int groups_p
             }
             for (int c = 0; c < r.n; ++c) add_slot(r.gene, 2 * n_groups + cta0 + c);
         } else {
-            // mixed region: ideal equal cuts snapped to the nearest gene boundary within len/16, so
-            // that only genes longer than len/8 are ever split across groups
-            const int64_t tol = (int64_t)floor(len / 16.0);
+            // mixed region: ideal equal-cost cuts snapped to the nearest gene boundary within snap * len, so that only
+            // genes longer than 2 * snap * len are ever split across groups (a split gene is a "late row" of the
+            // sampler kernel, bgh_tick2.cu: its leapfrog runs in the per-chain scalar phase)
+            const int64_t tol = (int64_t)floor(len * (snap > 0.0 ? snap : plan_snap()));
             int64_t prev = r.a;
             // cost of [r.a, x): SNPs + kappa * genes started; cuts equalise the cost
             auto cost = [&](int64_t x) {
@@ -207,7 +221,7 @@ int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_cta, int groups_p
             P.flags[(size_t)v] &= ~kOwner;
             if (P.off[(size_t)v] >= P.off[(size_t)v + 1]) continue;
             const int32_t g = gid[P.off[(size_t)v]];
-            if (g != owned_gene && !(g == 0 && first_partial)) P.flags[(size_t)v] |= kOwner;
+            if (g != owned_gene && !(g == 0 && first_partial) && !(g < n_replicated && !owns_replicated)) P.flags[(size_t)v] |= kOwner;
             owned_gene = g;
         }
     }
@@ -260,6 +274,7 @@ int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_cta, int groups_p
         int row = -1;
         if (g == 0 && first_partial) row = first_row;
         if (g == G - 1 && last_partial && last_row >= 0) row = last_row;
+        if (g < n_replicated) row = g;
         P.split_row.push_back(row);
         for (int32_t sl : lists[i]) P.split_slots.push_back(sl);
         P.split_ptr.push_back((int32_t)P.split_slots.size());
@@ -305,6 +320,26 @@ struct bgh_ctx {
     int* d_status = nullptr;
     int* d_ticks = nullptr;
     int* h_poll = nullptr;                   // pinned: {n_finished, status, ticks}
+    // fused persistent sampler (bgh_tick2.cu): command words, CTA partials, its own barrier word
+    unsigned char* d_t2 = nullptr;
+    size_t t2_bytes = 0;
+    // the sampler kernel's own work plan (bgh_tick2.cu): a gene boundary costs a leapfrog of the gene's row in all chains on
+    // top of the flush, and a gene split over SNP ranges is a "late row" handled by one CTA per chain, so its plan weighs
+    // boundaries higher (BGH_NUTS_KAPPA) and snaps every cut to a gene boundary (BGH_NUTS_SNAP) unless the gene is huge
+    Plan plan2;
+    int4* d_groups2 = nullptr;
+    int* d_split_gene2 = nullptr;
+    int* d_split_row2 = nullptr;
+    int* d_split_ptr2 = nullptr;
+    int* d_split_slots2 = nullptr;
+    std::vector<int32_t> own_ptr, own_gene;  // per CTA: the genes complete inside one of its SNP ranges (rows the CTA owns)
+    int* d_own_ptr = nullptr;
+    int* d_own_gene = nullptr;
+    unsigned int t2_epoch = 0;               // LL tags used so far by the per-chain peer exchange of the sampler ticks
+    unsigned int ll_eval_seq = 0;            // exchanges so far on the evaluation mailbox
+    bool peer_local = false;                 // peers are contexts of this process (bgh_peer_connect_local): nothing to unmap
+    bool dbg_send_only = false;              // tests: bgh_debug_peer_mode
+    int* d_gcoord = nullptr;                 // optional global coordinate of every local row (bgh_set_row_coords)
     bool fused = true;                       // BGH_UNFUSED=1 -> separate likelihood / finalize launches
     // peer-memory exchange of sharded contexts (bgh_peer_export / bgh_peer_connect)
     unsigned char* d_mailbox = nullptr;      // [flags 2 x kMaxPeers x 128 B][mail 2 x kMaxPeers x n doubles]
@@ -399,13 +434,16 @@ int bgh_create(bgh_ctx** out, const bgh_cfg* cfg)
         return fail(nullptr, BGH_EINVAL, "bgh_create: unknown model");
     if (cfg->model == BGH_MODEL_GENE_GAMMA && (!(cfg->gamma_rate > 0.0) || !isfinite(cfg->gamma_rate)))
         return fail(nullptr, BGH_EINVAL, "bgh_create: the gamma model needs gamma_rate = N_1kG > 0");
-    if (cfg->model == BGH_MODEL_GENE_GAMMA && cfg->n_shared_rows != 0)
-        return fail(nullptr, BGH_EINVAL, "bgh_create: the gamma model runs on single-rank contexts");
+    if (cfg->model == BGH_MODEL_GENE_GAMMA && cfg->n_shared_rows != cfg->n_replicated)
+        return fail(nullptr, BGH_EINVAL, "bgh_create: the gamma model shards with replicated genes only");
     if (cfg->n_genes <= 0 || (cfg->model == BGH_MODEL_GW_NORMAL && cfg->n_genes != 1))
         return fail(nullptr, BGH_EINVAL, "bgh_create: bad n_genes");
     if (!(cfg->c > 0.0) || !isfinite(cfg->c)) return fail(nullptr, BGH_EINVAL, "bgh_create: c must be positive");
     if (cfg->n_shared_rows < 0 || cfg->first_gene_row >= cfg->n_shared_rows || cfg->last_gene_row >= cfg->n_shared_rows)
         return fail(nullptr, BGH_EINVAL, "bgh_create: inconsistent shared-gene rows");
+    if (cfg->n_replicated < 0 || cfg->n_replicated > cfg->n_genes || cfg->n_replicated > 64 ||
+        (cfg->n_replicated > 0 && (cfg->n_shared_rows != cfg->n_replicated || cfg->first_gene_partial || cfg->last_gene_partial)))
+        return fail(nullptr, BGH_EINVAL, "bgh_create: inconsistent replicated genes (n_shared_rows must equal n_replicated <= 64)");
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -436,6 +474,7 @@ int bgh_create(bgh_ctx** out, const bgh_cfg* cfg)
     ctx->n_groups = ctx->n_cta * kLikWarps * (32 / ctx->CL);
     e = lik_configure();
     if (e == cudaSuccess) e = fused_configure();
+    if (e == cudaSuccess) e = tick2_configure();
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_bar, 256);
     if (e == cudaSuccess) e = cudaMemset(ctx->d_bar, 0, 256);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_status, sizeof(int));
@@ -463,10 +502,12 @@ void bgh_destroy(bgh_ctx* ctx)
     cudaFree(ctx->d_xs); cudaFree(ctx->d_xw); cudaFree(ctx->d_xl); cudaFree(ctx->d_gid); cudaFree(ctx->d_groups);
     cudaFree(ctx->d_slots); cudaFree(ctx->d_part); cudaFree(ctx->d_payload); cudaFree(ctx->d_cc);
     cudaFree(ctx->d_trace);
-    cudaFree(ctx->d_bar); cudaFree(ctx->d_status); cudaFree(ctx->d_ticks);
+    cudaFree(ctx->d_bar); cudaFree(ctx->d_status); cudaFree(ctx->d_ticks); cudaFree(ctx->d_t2);
+    cudaFree(ctx->d_own_ptr); cudaFree(ctx->d_own_gene); cudaFree(ctx->d_gcoord);
+    cudaFree(ctx->d_groups2); cudaFree(ctx->d_split_gene2); cudaFree(ctx->d_split_row2); cudaFree(ctx->d_split_ptr2); cudaFree(ctx->d_split_slots2);
     if (ctx->h_poll) cudaFreeHost(ctx->h_poll);
     for (int r = 0; r < kMaxPeers; ++r)
-        if (ctx->peer_base[r] && r != ctx->peer_rank) cudaIpcCloseMemHandle(ctx->peer_base[r]);
+        if (ctx->peer_base[r] && r != ctx->peer_rank && !ctx->peer_local) cudaIpcCloseMemHandle(ctx->peer_base[r]);
     cudaFree(ctx->d_mailbox);
     cudaFree(ctx->d_split_gene); cudaFree(ctx->d_split_row); cudaFree(ctx->d_split_ptr); cudaFree(ctx->d_split_slots);
     for (int i = 0; i < bgh_ctx::kPipe; ++i) {
@@ -611,10 +652,46 @@ int bgh_upload(bgh_ctx* ctx, const float* chi2, const float* ld, const int32_t* 
     const bool lp = gw ? true : ctx->cfg.last_gene_partial != 0;
     std::string err;
     int rc = build_plan(Mp, g_sorted.data(), G, ctx->n_cta, kLikWarps * (32 / ctx->CL), fp, lp, ctx->cfg.first_gene_row,
-                        ctx->cfg.last_gene_row, plan_kappa(), &ctx->plan, &err, kLikBatch);
+                        ctx->cfg.last_gene_row, plan_kappa(), &ctx->plan, &err, kLikBatch, ctx->cfg.n_replicated,
+                        ctx->cfg.owns_replicated != 0);
     if (rc != BGH_OK) return fail(ctx, rc, err);
 
+    {
+        const char* ek = getenv("BGH_NUTS_KAPPA");
+        const char* es = getenv("BGH_NUTS_SNAP");
+        rc = build_plan(Mp, g_sorted.data(), G, ctx->n_cta, kLikWarps * (32 / ctx->CL), fp, lp, ctx->cfg.first_gene_row,
+                        ctx->cfg.last_gene_row, (ek && *ek) ? atof(ek) : 60.0, &ctx->plan2, &err, kLikBatch, ctx->cfg.n_replicated,
+                        ctx->cfg.owns_replicated != 0, (es && *es) ? atof(es) : 0.5);
+        if (rc != BGH_OK) return fail(ctx, rc, err);
+    }
+    // rows each CTA owns in the fused sampler kernel (bgh_tick2.cu): genes complete inside one SNP range of the CTA
+    {
+        const Plan& P = ctx->plan2;
+        const int gpc = kLikWarps * (32 / ctx->CL);
+        ctx->own_ptr.assign((size_t)ctx->n_cta + 1, 0);
+        ctx->own_gene.clear();
+        for (int cta = 0; cta < ctx->n_cta; ++cta) {
+            for (int v = cta * gpc; v < (cta + 1) * gpc && !gw; ++v) {
+                const int32_t a = P.off[(size_t)v], b = P.off[(size_t)v + 1];
+                if (a >= b || (P.flags[(size_t)v] & kExclusive)) continue;
+                const int32_t gf = g_sorted[(size_t)a], gl = g_sorted[(size_t)b - 1];
+                for (int32_t g = gf; g <= gl; ++g) {
+                    if (g == gf && (P.flags[(size_t)v] & kHeadPartial)) continue;
+                    if (g == gl && (P.flags[(size_t)v] & kTailPartial)) continue;
+                    ctx->own_gene.push_back(g);
+                }
+            }
+            ctx->own_ptr[(size_t)cta + 1] = (int32_t)ctx->own_gene.size();
+        }
+    }
+
     auto dfree = [](auto*& p) { cudaFree(p); p = nullptr; };
+    dfree(ctx->d_own_ptr); dfree(ctx->d_own_gene);
+    BGH_CUDA(ctx, cudaMalloc(&ctx->d_own_ptr, sizeof(int) * ctx->own_ptr.size()));
+    BGH_CUDA(ctx, cudaMalloc(&ctx->d_own_gene, sizeof(int) * std::max<size_t>(ctx->own_gene.size(), 1)));
+    BGH_CUDA(ctx, cudaMemcpy(ctx->d_own_ptr, ctx->own_ptr.data(), sizeof(int) * ctx->own_ptr.size(), cudaMemcpyHostToDevice));
+    if (!ctx->own_gene.empty())
+        BGH_CUDA(ctx, cudaMemcpy(ctx->d_own_gene, ctx->own_gene.data(), sizeof(int) * ctx->own_gene.size(), cudaMemcpyHostToDevice));
     dfree(ctx->d_xs); dfree(ctx->d_xw); dfree(ctx->d_xl); dfree(ctx->d_gid); dfree(ctx->d_groups); dfree(ctx->d_slots);
     dfree(ctx->d_part); dfree(ctx->d_payload); dfree(ctx->d_cc); dfree(ctx->d_split_gene); dfree(ctx->d_split_row);
     dfree(ctx->d_split_ptr); dfree(ctx->d_split_slots);
@@ -662,15 +739,35 @@ int bgh_upload(bgh_ctx* ctx, const float* chi2, const float* ld, const int32_t* 
         BGH_CUDA(ctx, cudaMemcpy(ctx->d_split_slots, P.split_slots.data(), sizeof(int) * P.split_slots.size(), cudaMemcpyHostToDevice));
     }
     BGH_CUDA(ctx, cudaMemcpy(ctx->d_split_ptr, P.split_ptr.data(), sizeof(int) * (ns + 1), cudaMemcpyHostToDevice));
+    {
+        const Plan& P2 = ctx->plan2;
+        dfree(ctx->d_groups2); dfree(ctx->d_split_gene2); dfree(ctx->d_split_row2); dfree(ctx->d_split_ptr2); dfree(ctx->d_split_slots2);
+        for (int v = 0; v < ctx->n_groups; ++v)
+            groups[(size_t)v] = make_int4(P2.off[(size_t)v], P2.off[(size_t)v + 1], P2.flags[(size_t)v],
+                                          P2.off[(size_t)v] < P2.off[(size_t)v + 1] ? g_sorted[(size_t)P2.off[(size_t)v]] : 0);
+        const size_t ns2 = P2.split_gene.size();
+        BGH_CUDA(ctx, cudaMalloc(&ctx->d_groups2, sizeof(int4) * groups.size()));
+        BGH_CUDA(ctx, cudaMalloc(&ctx->d_split_gene2, sizeof(int) * std::max<size_t>(ns2, 1)));
+        BGH_CUDA(ctx, cudaMalloc(&ctx->d_split_row2, sizeof(int) * std::max<size_t>(ns2, 1)));
+        BGH_CUDA(ctx, cudaMalloc(&ctx->d_split_ptr2, sizeof(int) * (ns2 + 1)));
+        BGH_CUDA(ctx, cudaMalloc(&ctx->d_split_slots2, sizeof(int) * std::max<size_t>(P2.split_slots.size(), 1)));
+        BGH_CUDA(ctx, cudaMemcpy(ctx->d_groups2, groups.data(), sizeof(int4) * groups.size(), cudaMemcpyHostToDevice));
+        if (ns2) {
+            BGH_CUDA(ctx, cudaMemcpy(ctx->d_split_gene2, P2.split_gene.data(), sizeof(int) * ns2, cudaMemcpyHostToDevice));
+            BGH_CUDA(ctx, cudaMemcpy(ctx->d_split_row2, P2.split_row.data(), sizeof(int) * ns2, cudaMemcpyHostToDevice));
+            BGH_CUDA(ctx, cudaMemcpy(ctx->d_split_slots2, P2.split_slots.data(), sizeof(int) * P2.split_slots.size(), cudaMemcpyHostToDevice));
+        }
+        BGH_CUDA(ctx, cudaMemcpy(ctx->d_split_ptr2, P2.split_ptr.data(), sizeof(int) * (ns2 + 1), cudaMemcpyHostToDevice));
+    }
     ctx->uploaded = true;
     return BGH_OK;
 }
 
 static void fill_params(bgh_ctx* ctx, const double* q, double* grad, double* logp, double* payload,
-                        LikParams* lp, FinParams* fp)
+                        LikParams* lp, FinParams* fp, bool nuts_plan = false)
 {
     lp->sp = ctx->d_xs; lp->wp = ctx->d_xw; lp->lp = ctx->d_xl; lp->gid = ctx->d_gid; lp->groups = ctx->d_groups;
-    lp->q = q; lp->grad = grad; lp->ds = ctx->Cp; lp->cs = 1; fp->ds = ctx->Cp; fp->cs = 1; lp->slots = ctx->d_slots; lp->part = ctx->d_part; lp->cc = ctx->d_cc; lp->trace = ctx->d_trace;
+    lp->q = q; lp->grad = grad; lp->ds = ctx->Cp; lp->cs = 1; lp->woff = nullptr; fp->ds = ctx->Cp; fp->cs = 1; lp->slots = ctx->d_slots; lp->part = ctx->d_part; lp->cc = ctx->d_cc; lp->trace = ctx->d_trace;
     lp->Cp = ctx->Cp; lp->G = ctx->cfg.n_genes; lp->NG = ctx->n_groups; lp->n_cta = ctx->n_cta; lp->model = ctx->cfg.model;
     lp->fix = ctx->cfg.fix_intercept; lp->c = ctx->cfg.c; lp->gamma_rate = ctx->cfg.gamma_rate;
     fp->q = q; fp->grad = grad; fp->logp = logp; fp->slots = ctx->d_slots; fp->part = ctx->d_part; fp->cc = ctx->d_cc;
@@ -682,6 +779,12 @@ static void fill_params(bgh_ctx* ctx, const double* q, double* grad, double* log
     fp->first_gene_row = ctx->cfg.first_gene_row; fp->last_gene_row = ctx->cfg.last_gene_row;
     fp->G_local = ctx->cfg.n_genes;
     fp->n_shared_rows = ctx->cfg.n_shared_rows;
+    fp->n_replicated = ctx->cfg.n_replicated;
+    if (nuts_plan) {
+        lp->groups = ctx->d_groups2;
+        fp->split_gene = ctx->d_split_gene2; fp->split_row = ctx->d_split_row2; fp->split_ptr = ctx->d_split_ptr2;
+        fp->split_slots = ctx->d_split_slots2; fp->n_split = (int)ctx->plan2.split_gene.size(); fp->n_long = ctx->plan2.n_long;
+    }
 }
 
 static int run_sharded(bgh_ctx* ctx, const double* q, double* logp, double* grad, void* stream);
@@ -973,9 +1076,29 @@ static size_t mailbox_a_bytes(const bgh_ctx* ctx)
     const size_t b = kFlagBytes + 2 * (size_t)kMaxPeers * (size_t)(4 + ctx->cfg.n_shared_rows) * ctx->Cp * sizeof(double);
     return (b + 127) / 128 * 128;
 }
+static size_t mailbox_b_bytes(const bgh_ctx* ctx)
+{
+    const size_t b = kFlagBytes + 2 * (size_t)kMaxPeers * (size_t)kNutsMaxPartials * ctx->Cp * sizeof(double);
+    return (b + 127) / 128 * 128;
+}
+// LL-protocol regions of the per-chain exchange (bgh_tick2.cu): C = evaluation (4 + replicated genes values per chain),
+// D = sampler tick (kT2Nq + replicated genes values per chain); cells of 16 bytes, [2 parities][kMaxPeers][Cp][n_pay]
+static int ll_eval_pay(const bgh_ctx* ctx) { return kT2Lik + ctx->cfg.n_replicated; }
+static int ll_tick_pay(const bgh_ctx* ctx) { return kT2Nq + ctx->cfg.n_replicated; }
+static size_t mailbox_c_bytes(const bgh_ctx* ctx) { return 2 * (size_t)kMaxPeers * ctx->Cp * ll_eval_pay(ctx) * 16; }
+static size_t mailbox_d_bytes(const bgh_ctx* ctx) { return 2 * (size_t)kMaxPeers * ctx->Cp * ll_tick_pay(ctx) * 16; }
 static size_t mailbox_bytes(const bgh_ctx* ctx)
 {
-    return mailbox_a_bytes(ctx) + kFlagBytes + 2 * (size_t)kMaxPeers * (size_t)kNutsMaxPartials * ctx->Cp * sizeof(double);
+    return mailbox_a_bytes(ctx) + mailbox_b_bytes(ctx) + mailbox_c_bytes(ctx) + mailbox_d_bytes(ctx);
+}
+static void fill_ll_peer(const bgh_ctx* ctx, bool tick, T2Peer* pr)
+{
+    memset(pr, 0, sizeof(*pr));
+    const size_t off = mailbox_a_bytes(ctx) + mailbox_b_bytes(ctx) + (tick ? mailbox_c_bytes(ctx) : 0);
+    for (int r = 0; r < ctx->peer_world; ++r) pr->box[r] = reinterpret_cast<uint4*>(ctx->peer_base[r] + off);
+    pr->rank = ctx->peer_rank;
+    pr->world = ctx->peer_world < 1 ? 1 : ctx->peer_world;
+    pr->n_pay = tick ? ll_tick_pay(ctx) : ll_eval_pay(ctx);
 }
 
 int32_t bgh_peer_handle_bytes(void) { return (int32_t)sizeof(cudaIpcMemHandle_t); }
@@ -1017,6 +1140,46 @@ int bgh_peer_connect(bgh_ctx* ctx, int32_t rank, int32_t world, const void* hand
     ctx->peer_world = world;
     ctx->peer_epoch = 0;
     ctx->nuts_epoch = 0;
+    ctx->t2_epoch = 0;
+    ctx->ll_eval_seq = 0;
+    return BGH_OK;
+}
+
+int bgh_peer_connect_local(bgh_ctx* ctx, int32_t rank, int32_t world, bgh_ctx* const* peers)
+{
+    if (!ctx || !peers || world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+        return fail(ctx, BGH_EINVAL, "bgh_peer_connect_local: bad argument (at most 8 ranks)");
+    for (int r = 0; r < world; ++r) {
+        if (!peers[r] || !peers[r]->d_mailbox) return fail(ctx, BGH_ESTATE, "bgh_peer_connect_local: call bgh_peer_export on every rank first");
+        if (peers[r]->Cp != ctx->Cp || peers[r]->cfg.n_replicated != ctx->cfg.n_replicated || peers[r]->cfg.n_shared_rows != ctx->cfg.n_shared_rows)
+            return fail(ctx, BGH_EINVAL, "bgh_peer_connect_local: ranks disagree on the payload geometry");
+        ctx->peer_base[r] = peers[r]->d_mailbox;
+    }
+    if (peers[rank] != ctx) return fail(ctx, BGH_EINVAL, "bgh_peer_connect_local: peers[rank] must be this context");
+    ctx->peer_rank = rank;
+    ctx->peer_world = world;
+    ctx->peer_local = true;
+    ctx->peer_epoch = 0;
+    ctx->nuts_epoch = 0;
+    ctx->t2_epoch = 0;
+    ctx->ll_eval_seq = 0;
+    return BGH_OK;
+}
+
+int bgh_debug_peer_mode(bgh_ctx* ctx, int32_t send_only, int32_t seq)
+{
+    if (!ctx) return BGH_EINVAL;
+    ctx->dbg_send_only = send_only != 0;
+    if (seq >= 0) ctx->ll_eval_seq = (unsigned int)seq;
+    return BGH_OK;
+}
+
+int bgh_set_row_coords(bgh_ctx* ctx, const int32_t* global_coord)
+{
+    if (!ctx || !global_coord) return fail(ctx, BGH_EINVAL, "bgh_set_row_coords: null argument");
+    BGH_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    if (!ctx->d_gcoord) BGH_CUDA(ctx, cudaMalloc(&ctx->d_gcoord, sizeof(int) * (size_t)ctx->D));
+    BGH_CUDA(ctx, cudaMemcpy(ctx->d_gcoord, global_coord, sizeof(int) * (size_t)ctx->D, cudaMemcpyHostToDevice));
     return BGH_OK;
 }
 
@@ -1028,6 +1191,32 @@ static int run_sharded(bgh_ctx* ctx, const double* q, double* logp, double* grad
     FinParams fp;
     fill_params(ctx, q, grad, logp, ctx->d_payload, &lp, &fp);
     fp.finish_inline = 0;
+    if (ctx->cfg.n_replicated > 0 || ctx->cfg.n_shared_rows == 0) {
+        // replicated-gene sharding: one barrier, per-chain LL exchange issued by the chain CTAs (bgh_tick2.cu)
+        Eval2Params e;
+        e.lik = lp; e.fin = fp; e.bar = ctx->d_bar; e.status = ctx->d_status; e.chain_blocks = ctx->chain_blocks;
+        e.C = ctx->cfg.n_chains;
+        e.bar_base = ctx->bar_count;
+        ctx->bar_count += (unsigned long long)ctx->n_cta;
+        fill_ll_peer(ctx, false, &e.peer);
+        e.peer.epoch_base = 0;
+        e.peer.send_only = ctx->dbg_send_only ? 1 : 0;
+        e.epoch = ctx->ll_eval_seq++;
+        cudaStream_t s2 = (cudaStream_t)stream;
+        cudaEvent_t* ev2 = nullptr;
+        if (ctx->profiling && ctx->prof_n < bgh_ctx::kProfCap) {
+            ev2 = &ctx->prof_ev[3 * ctx->prof_n];
+            ctx->prof_n++;
+            BGH_CUDA(ctx, cudaEventRecord(ev2[0], s2));
+        }
+        BGH_CUDA(ctx, launch_eval2(e, ctx->CL, ctx->CPL, ctx->n_cta, s2));
+        if (ev2) {
+            BGH_CUDA(ctx, cudaEventRecord(ev2[1], s2));
+            BGH_CUDA(ctx, cudaEventRecord(ev2[2], s2));
+        }
+        ctx->launches += 1;
+        return BGH_OK;
+    }
     FusedParams f;
     f.lik = lp; f.fin = fp; f.bar = ctx->d_bar; f.status = ctx->d_status; f.chain_blocks = ctx->chain_blocks;
     f.bar_base = ctx->bar_count;
@@ -1103,11 +1292,12 @@ static int nuts_params(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nuts
     p->sums = buf->sums; p->logp_w = buf->logp_w; p->n_active = buf->n_active_dev;
     p->D = ctx->D; p->Cp = ctx->Cp; p->C = ctx->cfg.n_chains; p->n_vec_blocks = 2 * ctx->sm_count;
     p->coord_offset = cfg->coord_offset; p->seed = cfg->seed; p->draw = draw;
-    p->head_rows = 0; p->own_head = 1; p->own_first = 1; p->status = ctx->d_status;
+    p->head_rows = 0; p->own_head = 1; p->own_first = 1; p->status = ctx->d_status; p->gcoord = ctx->d_gcoord;
     memset(&p->peer, 0, sizeof(p->peer));
     if (sharded) {
         // rows in front of the per-gene block (the whole vector in the genome-wide model) are replicated
         p->head_rows = ctx->cfg.model == BGH_MODEL_GW_NORMAL ? ctx->D : (ctx->cfg.model == BGH_MODEL_GENE_GAMMA ? 2 : 3);
+        if (ctx->cfg.model != BGH_MODEL_GW_NORMAL) p->head_rows += ctx->cfg.n_replicated;   // replicated genes are replicated rows
         p->own_head = ctx->peer_rank == 0 ? 1 : 0;
         p->own_first = ctx->cfg.first_gene_partial ? 0 : 1;
         for (int r = 0; r < ctx->peer_world; ++r) {
@@ -1211,6 +1401,132 @@ int bgh_nuts_transition(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nut
     return BGH_OK;
 }
 
+// The fused persistent sampler (bgh_tick2.cu): state stays gene-major [slot][D][Cp]; two grid barriers per tick.
+static int nuts_run_tick2(bgh_ctx* ctx, const bgh_nuts_async_buffers* buf, const bgh_nuts_cfg* cfg, AsyncParams a, int poll_ticks,
+                          cudaStream_t s, int64_t* n_ticks)
+{
+    const size_t vec = (size_t)ctx->D * ctx->Cp;
+    const int Dtot = cfg->n_dim_total > 0 ? cfg->n_dim_total : ctx->D;
+    const double step0 = cfg->step_scale / pow((double)Dtot, 0.25);
+    if ((int)ctx->plan2.split_gene.size() > 8192)
+        return fail(ctx, BGH_EINVAL, "bgh_nuts_run: more than 8192 genes are split over several SNP ranges");
+    // scratch: [barrier 256 B][cmd_h Cp doubles][cmd_bits Cp ints][cmd_woff Cp ints][partials n_cta x kAsyncPartials x Cp doubles]
+    const size_t off_h = 256, off_b = off_h + sizeof(double) * ctx->Cp, off_w = off_b + sizeof(int) * ctx->Cp;
+    const size_t off_p = (off_w + sizeof(int) * ctx->Cp + 255) / 256 * 256;
+    const size_t need = off_p + sizeof(double) * (size_t)ctx->n_cta * kAsyncPartials * ctx->Cp;
+    if (ctx->t2_bytes < need) {
+        cudaFree(ctx->d_t2);
+        ctx->d_t2 = nullptr;
+        ctx->t2_bytes = 0;
+        BGH_CUDA(ctx, cudaMalloc(&ctx->d_t2, need));
+        ctx->t2_bytes = need;
+    }
+    BGH_CUDA(ctx, cudaMemsetAsync(ctx->d_t2, 0, need, s));
+    BGH_CUDA(ctx, nuts_async_launch_init(a, step0, 10.0, s, false));
+    ctx->launches += 1;
+    // the two role-swapped buffers X0 = (QL, PL, GL), X1 = (QR, PR, GR): a finite start for every chain (padded chains
+    // included); the first tick initialises both from Q / GRAD
+    double* const q0 = buf->base.state + kSlotQL * vec;
+    double* const g0 = buf->base.state + kSlotGL * vec;
+    for (int which = 0; which < 2; ++which) {
+        const size_t o = (size_t)which * (kSlotQR - kSlotQL) * vec;
+        BGH_CUDA(ctx, cudaMemcpyAsync(q0 + o, buf->base.state + kSlotQP * vec, sizeof(double) * vec, cudaMemcpyDeviceToDevice, s));
+        BGH_CUDA(ctx, cudaMemcpyAsync(g0 + o, buf->base.state + kSlotGP * vec, sizeof(double) * vec, cudaMemcpyDeviceToDevice, s));
+        BGH_CUDA(ctx, cudaMemsetAsync(buf->base.state + kSlotPL * vec + o, 0, sizeof(double) * vec, s));
+    }
+
+    // reserve the persisting share of the L2 for the vectors every tick re-reads (evict-last hints in bgh_tick2.cu)
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, ctx->cfg.device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+            const char* e = getenv("BGH_L2_PERSIST_MB");
+            size_t want = e ? (size_t)atoi(e) << 20 : 0;    // measured: reserving the persisting share makes the tick slower
+            if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            if (getenv("BGH_T2_VERBOSE")) fprintf(stderr, "# persisting L2: max %d MB, reserved %zu MB, L2 %d MB\n",
+                                                  prop.persistingL2CacheMaxSize >> 20, want >> 20, prop.l2CacheSize >> 20);
+        }
+        cudaGetLastError();
+    }
+    Tick2Params t;
+    memset(&t, 0, sizeof(t));
+    fill_params(ctx, q0, g0, buf->base.logp_w, ctx->d_payload, &t.lik, &t.fin, true);
+    t.fin.finish_inline = 1;
+    t.lik.trace = nullptr;
+    t.a = a;
+    t.a.n.n_vec_blocks = ctx->n_cta;
+    t.bar = reinterpret_cast<unsigned long long*>(ctx->d_t2);
+    t.status = ctx->d_status;
+    t.chain_blocks = ctx->chain_blocks;
+    t.n_ticks = poll_ticks;
+    t.ticks_done = ctx->d_ticks;
+    t.first_launch = 1;
+    t.tick_base = 0;
+    t.row0 = ctx->cfg.model == BGH_MODEL_GENE_NORMAL ? 3 : 2;
+    t.n_unowned = 0;
+    t.cmd_h = reinterpret_cast<double*>(ctx->d_t2 + off_h);
+    t.cmd_bits = reinterpret_cast<int*>(ctx->d_t2 + off_b);
+    t.cmd_woff = reinterpret_cast<int*>(ctx->d_t2 + off_w);
+    t.lik.woff = t.cmd_woff;
+    t.part = reinterpret_cast<double*>(ctx->d_t2 + off_p);
+    t.cta_row_ptr = ctx->d_own_ptr;
+    t.cta_row_gene = ctx->d_own_gene;
+    { const char* e = getenv("BGH_T2_TRACE_CTA"); t.trace_cta = e ? atoi(e) : 0; }
+    { const char* e = getenv("BGH_TRACE_TICK"); t.trace_first = e ? atoi(e) : 0; }
+    t.k6 = buf->k6;
+    fill_ll_peer(ctx, true, &t.peer);
+    t.peer.epoch_base = ctx->t2_epoch;
+    t.phase_trace = ctx->d_trace;   // NULL unless bgh_debug_trace enabled it (tools/time_tick2.py)
+
+    const int64_t max_ticks = (int64_t)(a.tune + a.draws) * 1024 + 1024;
+    int64_t ticks = 0;
+    int status = BGH_OK;
+    BGH_CUDA(ctx, cudaMemsetAsync(ctx->d_ticks, 0, sizeof(int), s));
+    while (ticks < max_ticks) {
+        cudaError_t e = cudaMemsetAsync(t.bar, 0, 8, s);
+        if (e == cudaSuccess) e = launch_tick2(t, ctx->CL, ctx->CPL, ctx->n_cta, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&ctx->h_poll[0], buf->base.n_active_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&ctx->h_poll[1], ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&ctx->h_poll[2], ctx->d_ticks, sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { status = fail(ctx, BGH_ECUDA, std::string("bgh_nuts_run: ") + cudaGetErrorString(e)); break; }
+        ctx->launches += 1;
+        ticks = ctx->h_poll[2];
+        t.tick_base = (int)ticks;
+        t.first_launch = 0;
+        if (ctx->h_poll[1] != 0) {
+            cudaMemset(ctx->d_status, 0, sizeof(int));
+            status = fail(ctx, BGH_ECUDA, ctx->h_poll[1] == 2 ? "bgh_nuts_run: a peer GPU did not answer inside the tick kernel"
+                                                               : "bgh_nuts_run: grid barrier timed out inside the tick kernel");
+            break;
+        }
+        *buf->base.n_active_host = ctx->h_poll[0];
+        if (ctx->h_poll[0] >= ctx->cfg.n_chains) break;
+    }
+    ctx->t2_epoch += (unsigned int)ticks + 1u;
+    cudaCtxResetPersistingL2Cache();
+    cudaGetLastError();
+    if (status == BGH_OK && ticks >= max_ticks) status = fail(ctx, BGH_ESTATE, "bgh_nuts_run: tick budget exhausted");
+    if (n_ticks) *n_ticks = ticks;
+    return status;
+}
+
+// Which persistent kernel runs bgh_nuts_run.  BGH_TICK=1 / 2 forces nuts_tick_kernel (bgh_fused.cu) / the fused kernel
+// (bgh_tick2.cu).  Default: the fused kernel — sharded contexts and streaming statistics need it, and it wins wherever a
+// rank's sampler state fits the L2 — except on a single rank whose state is far larger than the L2 (1.1M x 15k x 64 chains:
+// both kernels stream the state from HBM there and the round-1 kernel's chain-major sweeps are ~15% faster).
+static bool tick_v1(const bgh_ctx* ctx = nullptr, bool needs_v2 = false)
+{
+    const char* e = getenv("BGH_TICK");
+    if (e && *e == '1') return true;
+    if (e && *e == '2') return false;
+    const char* o = getenv("BGH_TICK_V1");
+    if (o && *o == '1') return true;
+    if (o && *o == '0') return false;
+    if (!ctx || needs_v2) return false;
+    return sizeof(double) * (size_t)ctx->D * ctx->Cp > (size_t)4 << 20;
+}
+
 int bgh_nuts_run(bgh_ctx* ctx, const bgh_nuts_async_buffers* buf, const bgh_nuts_cfg* cfg, int32_t tune,
                  int32_t draws, int32_t poll_ticks, void* stream, int64_t* n_ticks)
 {
@@ -1218,10 +1534,11 @@ int bgh_nuts_run(bgh_ctx* ctx, const bgh_nuts_async_buffers* buf, const bgh_nuts
     AsyncParams a;
     int rc = nuts_params(ctx, &buf->base, cfg, 0, &a.n);
     if (rc != BGH_OK) return rc;
-    if (a.n.peer.world > 1)
-        return fail(ctx, BGH_ESTATE, "bgh_nuts_run: the persistent tick kernel runs on single-rank contexts; "
-                                     "sharded contexts use bgh_nuts_transition");
-    if (!buf->afl || (draws > 0 && !buf->trace) || tune < 0 || draws < 0 || tune + draws <= 0)
+    const bool needs_v2 = a.n.peer.world > 1 || buf->k6 != nullptr || !buf->trace;
+    if (a.n.peer.world > 1 && (tick_v1(ctx, true) || (ctx->cfg.n_shared_rows != ctx->cfg.n_replicated)))
+        return fail(ctx, BGH_ESTATE, "bgh_nuts_run: sharded contexts need replicated-gene sharding (n_replicated) and the fused "
+                                     "sampler kernel; other sharded contexts use bgh_nuts_transition");
+    if (!buf->afl || (draws > 0 && !buf->trace && !buf->k6) || tune < 0 || draws < 0 || tune + draws <= 0)
         return fail(ctx, BGH_EINVAL, "bgh_nuts_run: bad argument");
     if (ctx->Cp > 128) return fail(ctx, BGH_EINVAL, "bgh_nuts_run: at most 128 chains per context (use several contexts / GPUs)");
     if (poll_ticks <= 0) poll_ticks = 64;
@@ -1241,6 +1558,8 @@ int bgh_nuts_run(bgh_ctx* ctx, const bgh_nuts_async_buffers* buf, const bgh_nuts
     const double step0 = cfg->step_scale / pow((double)Dtot, 0.25);
     if (ctx->cfg.n_chains > ctx->n_cta) return fail(ctx, BGH_EINVAL, "bgh_nuts_run: more chains than CTAs");
     if (!ctx->fused) return fail(ctx, BGH_ESTATE, "bgh_nuts_run: needs the cooperative kernels (BGH_UNFUSED is set or the device cannot co-schedule the grid)");
+    if (!tick_v1(ctx, needs_v2)) return nuts_run_tick2(ctx, buf, cfg, a, poll_ticks, s, n_ticks);
+    if (buf->k6 || !buf->trace) return fail(ctx, BGH_EINVAL, "bgh_nuts_run: BGH_TICK_V1 needs a trace and has no streaming statistics");
     BGH_CUDA(ctx, nuts_async_launch_init(a, step0, 10.0, s));
     ctx->launches += 1;
     // Inside the run the sampler state is chain-major ([slot][Cp][D], see bgh_fused.cu): convert the slots

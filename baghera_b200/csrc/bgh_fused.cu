@@ -19,6 +19,7 @@
 
 #include "bgh_fin_device.cuh"
 #include "bgh_fused.h"
+#include "bgh_grid_device.cuh"
 #include "bgh_internal.h"
 #include "bgh_lik_device.cuh"
 #include "bgh_peer_device.cuh"
@@ -36,59 +37,6 @@
 #endif
 
 namespace bgh {
-
-// ---------------------------------------------------------------------------------------------
-// grid barrier: one monotonic 64-bit arrival counter (release-add, acquire-spin).  Requires all CTAs to
-// be co-resident (cooperative launch).  A CTA that
-// waits longer than kBarrierTimeoutNs raises *status and returns so that a logic error cannot hang
-// the GPU; the host then reports the failure and resets the barrier words.
-// ---------------------------------------------------------------------------------------------
-constexpr unsigned long long kBarrierTimeoutNs = 2000000000ull;
-
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
-{
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v)
-{
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ int ld_volatile_i32(const int* p)
-{
-    int v;
-    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// `target` is thread 0's running arrival target: the host passes the counter value at launch
-// (FusedParams.bar_base, it knows how many barriers every launch executes) and every barrier adds gridDim.x.
-__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long& target, int* status)
-{
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        target += gridDim.x;
-        unsigned long long old;
-        asm volatile("atom.add.release.gpu.global.u64 %0, [%1], %2;" : "=l"(old) : "l"(bar), "l"(1ull) : "memory");
-        if (old + 1 < target) {
-            const unsigned long long t0 = global_timer_ns();
-            unsigned spins = 0;
-            while (true) {
-                unsigned long long v;
-                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
-                if (v >= target) break;
-                if ((++spins & 1023u) == 0 && (global_timer_ns() - t0 > kBarrierTimeoutNs || ld_volatile_i32(status) != 0)) {
-                    atomicExch(status, 1);
-                    break;
-                }
-            }
-        } else {
-            asm volatile("fence.acq_rel.gpu;" ::: "memory");
-        }
-    }
-    __syncthreads();
-}
 
 // ---------------------------------------------------------------------------------------------
 // finalize, spread over the resident CTAs (all sums in a fixed order -> bit-reproducible):
@@ -139,7 +87,7 @@ __device__ __forceinline__ void fin_phase(const FinParams& p, unsigned char* sme
             if (on) p.payload[(size_t)which * Cp + ch] = acc;   // rows 0..3 of the payload are [4][Cp]
             // the all-reduce leaves TOTALS in the payload: rows of rank-shared genes this rank does not hold
             // must contribute zero to the next exchange
-            if (on && which == 0 && !p.finish_inline)
+            if (on && which == 0 && !p.finish_inline && p.n_replicated == 0)
                 for (int r = 0; r < p.n_shared_rows; ++r)
                     if (r != p.first_gene_row && r != p.last_gene_row) p.payload[(size_t)(4 + r) * Cp + ch] = 0.0;
         }
@@ -264,6 +212,8 @@ __global__ void __launch_bounds__(kLikThreads, 1) logp_grad_sharded_kernel(const
         s.S1 = p.payload[2 * Cp + ch];
         s.S2 = p.payload[3 * Cp + ch];
         finish_chain(p, ch, s, chain_const(p, ch));
+        for (int j = 0; j < p.n_replicated; ++j)
+            finish_gene(p, j, ch, p.payload[(size_t)(4 + j) * Cp + ch], load_gene_coef(p, j, ch, true));
         if (p.first_gene_row >= 0)
             finish_gene(p, 0, ch, p.payload[(size_t)(4 + p.first_gene_row) * Cp + ch], load_gene_coef(p, 0, ch, true));
         if (p.last_gene_row >= 0 && !(p.G_local == 1 && p.first_gene_row >= 0))

@@ -51,7 +51,7 @@ struct Plan {
 // (the upload pads every gene to a multiple of the kernel's batch, so gene boundaries already are).
 int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_cta, int groups_per_cta,
                bool first_partial, bool last_partial, int first_row, int last_row, double kappa,
-               Plan* plan, std::string* err, int align = 1);
+               Plan* plan, std::string* err, int align = 1, int n_replicated = 0, bool owns_replicated = true, double snap = 0.0);
 
 struct LikParams {
     const double* sp;     // prepared SoA, gene sorted: s / sqrt(l)
@@ -62,6 +62,7 @@ struct LikParams {
     const double* q;      // element (row d, chain c) at q[d * ds + c * cs]: [D][Cp] (ds = Cp, cs = 1) for the
     double* grad;         // evaluation API, chain-major [Cp][D] (ds = 1, cs = D) inside the tick kernel
     long long ds, cs;
+    const int* woff;      // optional [Cp]: per-chain element offset added to every q / grad access (sampler kernel), or NULL
     double* slots;        // [2*NG + nCTA][Cp]
     double* part;         // [nCTA][4][Cp]
     double* cc;           // [2][Cp] per-chain constants {1/W^2, mi} written for finalize
@@ -103,6 +104,7 @@ struct FinParams {
     // finish-only
     int first_gene_row, last_gene_row, G_local;
     int n_shared_rows;    // payload rows 4.. : a row of a rank-shared gene this rank does NOT hold is zeroed every launch
+    int n_replicated;     // genes [0, n_replicated) are held by every rank: payload row 4 + j <-> gene j
 };
 
 // kernel launchers (bgh_lik.cu)

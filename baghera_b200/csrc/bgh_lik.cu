@@ -177,6 +177,8 @@ __global__ void finish_kernel(const FinParams p)
     s.S1 = p.payload[2 * Cp + ch];
     s.S2 = p.payload[3 * Cp + ch];
     finish_chain(p, ch, s, chain_const(p, ch));
+    for (int j = 0; j < p.n_replicated; ++j)
+        finish_gene(p, j, ch, p.payload[(size_t)(4 + j) * Cp + ch], load_gene_coef(p, j, ch, true));
     if (p.first_gene_row >= 0)
         finish_gene(p, 0, ch, p.payload[(size_t)(4 + p.first_gene_row) * Cp + ch], load_gene_coef(p, 0, ch, true));
     if (p.last_gene_row >= 0 && !(p.G_local == 1 && p.first_gene_row >= 0))

@@ -184,12 +184,16 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
     const int4 desc = p.groups[v];
     const long long ds = p.ds, cs = p.cs;
     double q0[CPL], q1[CPL], q2[CPL];
+    // sampler kernel (bgh_tick2.cu): every chain reads its position from / writes its gradient to one of two
+    // role-swapped buffers; wo[k] is the chain's element offset into q / grad (0 when p.woff is NULL)
+    long long wo[CPL];
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
         const int ch = ch0 + k * CL;
-        q0[k] = p.q[0 * ds + ch * cs];
-        q1[k] = p.q[1 * ds + ch * cs];
-        q2[k] = (gene_model && !gamma_model) ? p.q[2 * ds + ch * cs] : 0.0;
+        wo[k] = p.woff != nullptr ? (long long)p.woff[ch] : 0ll;
+        q0[k] = p.q[0 * ds + ch * cs + wo[k]];
+        q1[k] = p.q[1 * ds + ch * cs + wo[k]];
+        q2[k] = (gene_model && !gamma_model) ? p.q[2 * ds + ch * cs + wo[k]] : 0.0;
     }
     const int ra = desc.x, rb = desc.y, flags = desc.z, g_first = desc.w;
     const bool exclusive = (flags & kExclusive) != 0;
@@ -223,8 +227,8 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
     if (active && gene_model) {
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
-            braw[k] = beta[(long long)g_first * ds + (long long)(k * CL) * cs];
-            bn[k] = (g_first + 1 < p.G) ? beta[(long long)(g_first + 1) * ds + (long long)(k * CL) * cs] : 0.0;
+            braw[k] = beta[(long long)g_first * ds + (long long)(k * CL) * cs + wo[k]];
+            bn[k] = (g_first + 1 < p.G) ? beta[(long long)(g_first + 1) * ds + (long long)(k * CL) * cs + wo[k]] : 0.0;
         }
     }
 
@@ -279,7 +283,7 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
 #pragma unroll
             for (int k = 0; k < CPL; ++k) {
                 if (gene_model)
-                    dst[k] = (g < p.G) ? beta[(long long)g * ds + (long long)(k * CL) * cs] : 0.0;
+                    dst[k] = (g < p.G) ? beta[(long long)g * ds + (long long)(k * CL) * cs + wo[k]] : 0.0;
                 else
                     dst[k] = mi[k];
             }
@@ -303,11 +307,11 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
                     // d/d beta_log = beta (c sum r - rate) + mi       (prior + log-Jacobian + likelihood)
                     double* dst = p.grad + (long long)(row0 + cur) * ds + (long long)ch0 * cs;
 #pragma unroll
-                    for (int k = 0; k < CPL; ++k) dst[(long long)(k * CL) * cs] = fma(nb[k] * neg_inv_c, fma(p.c, ag[k], -p.gamma_rate), mi[k]);
+                    for (int k = 0; k < CPL; ++k) dst[(long long)(k * CL) * cs + wo[k]] = fma(nb[k] * neg_inv_c, fma(p.c, ag[k], -p.gamma_rate), mi[k]);
                 } else if (gene_model) {
                     double* dst = p.grad + (long long)(row0 + cur) * ds + (long long)ch0 * cs;
 #pragma unroll
-                    for (int k = 0; k < CPL; ++k) dst[(long long)(k * CL) * cs] = fma(p.c, ag[k], -db[k] * iW2[k]);
+                    for (int k = 0; k < CPL; ++k) dst[(long long)(k * CL) * cs + wo[k]] = fma(p.c, ag[k], -db[k] * iW2[k]);
                 }
                 owner = !to_head;   // this group holds the gene's first SNP: it owns the prior terms
             }

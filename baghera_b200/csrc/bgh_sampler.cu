@@ -55,6 +55,7 @@ __device__ __forceinline__ VecIdx vec_index(const NutsParams& p)
 // sharded runs: global coordinate of local row d, and whether this rank counts row d in the per-chain sums
 __device__ __forceinline__ unsigned global_coord(const NutsParams& p, int d)
 {
+    if (p.gcoord != nullptr) return (unsigned)p.gcoord[d];
     return (unsigned)(d >= p.head_rows ? d + p.coord_offset : d);
 }
 __device__ __forceinline__ bool row_owned(const NutsParams& p, int d)
@@ -677,9 +678,9 @@ __global__ void nuts_async_zgen_kernel(const AsyncParams a)
     }
 }
 
-cudaError_t nuts_async_launch_init(const AsyncParams& a, double step0, double initial_weight, cudaStream_t s)
+cudaError_t nuts_async_launch_init(const AsyncParams& a, double step0, double initial_weight, cudaStream_t s, bool fill_z)
 {
-    nuts_async_zgen_kernel<<<a.n.n_vec_blocks, 256, 0, s>>>(a);
+    if (fill_z) nuts_async_zgen_kernel<<<a.n.n_vec_blocks, 256, 0, s>>>(a);   // nuts_tick_kernel only (bgh_tick2.cu draws its normals in place)
     nuts_async_init_kernel<<<(a.n.Cp + 127) / 128, 128, 0, s>>>(a, step0, initial_weight);
     return cudaGetLastError();
 }

@@ -59,6 +59,7 @@ struct NutsParams {
     // first gene row on the lower rank when the gene continues from it (own_first = 0).  Single rank:
     // head_rows = 0, coord_offset = 0, own_* = 1, peer.world <= 1.
     int coord_offset, head_rows, own_head, own_first;
+    const int* gcoord;  // optional [D]: global coordinate of every local row (bgh_set_row_coords), or NULL
     PeerParams peer;    // sums are all-reduced over peer memory inside the scalar kernels when peer.world > 1
     int* status;        // device status word (peer time-out), may be NULL on a single rank
     unsigned long long seed;
@@ -105,6 +106,6 @@ struct AsyncParams {
     int tune, draws;
     int early_draws, early_depth, max_depth, window;
 };
-cudaError_t nuts_async_launch_init(const AsyncParams& p, double step0, double initial_weight, cudaStream_t s);   // leap1, leap2, leaf scalar (plus the likelihood + finalize)
+cudaError_t nuts_async_launch_init(const AsyncParams& p, double step0, double initial_weight, cudaStream_t s, bool fill_z = true);   // leap1, leap2, leaf scalar (plus the likelihood + finalize)
 
 }  // namespace bgh

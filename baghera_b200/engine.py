@@ -138,6 +138,19 @@ class Engine:
         buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
         check(self.L.bgh_peer_connect(self.ctx, int(rank), int(world), ctypes.cast(buf, ctypes.c_void_p)), self.ctx)
 
+    def peer_connect_local(self, rank, engines):
+        """Ranks as engines of this process (tests emulating the ranks on one GPU; one process driving several GPUs)."""
+        arr = (ctypes.c_void_p * len(engines))(*[e.ctx for e in engines])
+        check(self.L.bgh_peer_connect_local(self.ctx, int(rank), len(engines), arr), self.ctx)
+
+    def debug_peer_mode(self, send_only, seq=-1):
+        check(self.L.bgh_debug_peer_mode(self.ctx, int(bool(send_only)), int(seq)), self.ctx)
+
+    def set_row_coords(self, coords):
+        c = np.ascontiguousarray(coords, dtype=np.int32)
+        assert c.shape == (self.D,), (c.shape, self.D)
+        check(self.L.bgh_set_row_coords(self.ctx, c.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))), self.ctx)
+
     def logp_grad_sharded(self, q_dc, logp, grad):
         """One launch per rank: local pass + one-shot all-reduce over peer memory + closing formulas."""
         check(self.L.bgh_logp_grad_sharded(self.ctx, _ptr(q_dc), _ptr(logp), _ptr(grad), self._stream()), self.ctx)

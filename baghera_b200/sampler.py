@@ -28,10 +28,11 @@ EARLY_MAX_TREEDEPTH, MAX_TREEDEPTH, EARLY_DRAWS = 8, 10, 200
 
 
 class NutsSampler:
-    def __init__(self, engine, seed=20211, target_accept=0.90, gene_lo=0, n_dim_total=0):
-        """gene_lo / n_dim_total: gene-block sharded engines only (``Shard.gene_lo`` and the global D): every
-        rank runs its own NutsSampler over its rows of q; the per-chain sums are all-reduced over NVLink peer
-        memory inside the sampler's kernels, so all ranks take identical decisions (lock-step driver only)."""
+    def __init__(self, engine, seed=20211, target_accept=0.90, row_coords=None, n_dim_total=0):
+        """row_coords / n_dim_total: gene-block sharded engines only (``Shard.row_coords()`` and the global D): every
+        rank runs its own NutsSampler over its rows of q; the per-chain sums are exchanged over NVLink peer memory
+        inside the sampler's kernels and the momentum normals are keyed by the global coordinate, so all ranks take
+        identical decisions and reproduce the single-GPU chains."""
         import torch
 
         self.eng = engine
@@ -62,8 +63,10 @@ class NutsSampler:
         self.L.bgh_nuts_cfg_default(ctypes.byref(cfg))
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.target_accept = float(target_accept)
-        cfg.coord_offset = int(gene_lo)
+        cfg.coord_offset = 0
         cfg.n_dim_total = int(n_dim_total)
+        if row_coords is not None:
+            engine.set_row_coords(row_coords)
         self.cfg = cfg
         self.draw = 0
         self.n_adapt = 0

@@ -73,9 +73,12 @@ typedef struct bgh_cfg {
     int32_t last_gene_row;     /* payload row of the last gene if rank-shared, else -1 */
     int32_t n_shared_rows;     /* rank-shared genes over all ranks (payload rows 4 .. 4+n-1) */
     int32_t sm_count_override; /* 0 = query the device; tests may set it to build partitions on CPU */
-    int32_t reserved0;
+    int32_t n_replicated;      /* gene-block sharding with REPLICATED genes: this shard's genes [0, n_replicated) are held (with
+                                * a share of their SNPs) by EVERY rank; gene j travels in payload row j (n_shared_rows must
+                                * equal n_replicated, first/last_gene_* stay 0 / -1).  Their rows of q are replicated too. */
     double  gamma_rate;        /* BGH_MODEL_GENE_GAMMA: rate of the Gamma(mi, rate) prior = N_1kG (gene_regression.py:231) */
-    int32_t reserved[2];
+    int32_t owns_replicated;   /* 1 on the one rank (rank 0) that counts the replicated genes' prior terms */
+    int32_t reserved;
 } bgh_cfg;
 
 /* Fills *cfg with single-GPU defaults. */
@@ -133,6 +136,13 @@ int32_t bgh_peer_handle_bytes(void);
 int bgh_peer_export(bgh_ctx* ctx, void* handle_out);
 int bgh_peer_connect(bgh_ctx* ctx, int32_t rank, int32_t world, const void* handles);
 int bgh_logp_grad_sharded(bgh_ctx* ctx, const double* q, double* logp, double* grad, void* stream);
+/* Ranks as contexts of ONE process (several GPUs driven by one process, or tests that emulate the ranks one after the other
+ * on one GPU): peers[r] is rank r's context (bgh_peer_export already called on each). */
+int bgh_peer_connect_local(bgh_ctx* ctx, int32_t rank, int32_t world, bgh_ctx* const* peers);
+/* Tests only: send_only != 0 makes the next evaluations deposit their payload in the peers' mailboxes without waiting for
+ * the peers' (results are garbage) — a single GPU can then run the ranks one after the other: every rank once send-only,
+ * then every rank normally with the same sequence number.  seq >= 0 sets the mailbox sequence number of the next evaluation. */
+int bgh_debug_peer_mode(bgh_ctx* ctx, int32_t send_only, int32_t seq);
 int bgh_peer_status(bgh_ctx* ctx, int32_t* status);
 
 /* B1' with HOST buffers in PyMC3's layout: q[C][D] -> logp[C], grad[C][D].  Copies H2D, transposes
@@ -205,7 +215,7 @@ int bgh_debug_plan(int64_t M, const int32_t* gid_sorted, int32_t G, int32_t n_ct
 #define BGH_NUTS_SC_LOGP 1
 #define BGH_NUTS_N_FL 11
 #define BGH_NUTS_N_STATS 8
-#define BGH_NUTS_ASYNC_N_FL 24
+#define BGH_NUTS_ASYNC_N_FL 26
 #define BGH_NUTS_ASYNC_N_SC 24
 #define BGH_NUTS_ASYNC_PARTIALS (2 * BGH_NUTS_MAX_DEPTH + 4)
 
@@ -256,6 +266,11 @@ int bgh_nuts_transition(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nut
                         int32_t tune, int32_t max_treedepth, double fg_weight, double bg_weight,
                         int32_t switch_window, void* stream, int32_t* n_leapfrogs);
 
+/* Sharded contexts: global coordinate of every local row of q (host int32[D]); the momentum normals are Philox draws keyed
+ * by the GLOBAL coordinate, so a sharded run reproduces the single-GPU chains.  Default: row d -> d (+ coord_offset behind
+ * the head rows). */
+int bgh_set_row_coords(bgh_ctx* ctx, const int32_t* global_coord);
+
 /* End of tuning: step size <- exp(log_step_bar) (DualAverageAdaptation.current(tune=False)). */
 int bgh_nuts_stop_tuning(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nuts_cfg* cfg, void* stream);
 
@@ -269,9 +284,6 @@ int bgh_nuts_stop_tuning(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nu
  * BGH_NUTS_ASYNC_PARTIALS quantities per block; plus
  *   afl      int32[BGH_NUTS_ASYNC_N_FL][Cp]
  *   trace    [draws][C][D] fp64 (trace_f32 = 0) or fp32: positions after each post-tuning transition
- *            (chain-major: inside the run the state is kept chain-major so that every per-chain vector
- *            operation of the tree bookkeeping is a contiguous stream; Q / GRAD / VAR and the adaptation
- *            slots are converted from and back to the [D][Cp] layout at the start / end of the call)
  *   stats    double[tune + draws][BGH_NUTS_N_STATS][C]
  * Call bgh_nuts_init first (start point, mass-matrix slots); then bgh_nuts_run once. */
 typedef struct bgh_nuts_async_buffers {
@@ -281,6 +293,10 @@ typedef struct bgh_nuts_async_buffers {
     double* run_stats;
     int32_t trace_f32;
     int32_t reserved;
+    double* k6;     /* optional [3][D][Cp] (zeroed by the caller): streaming per-coordinate sums over the recorded draws
+                     * {sum v, sum v^2, count(v - mi > 0)}, v = beta_g (normal model) or N_1kG * beta_g (gamma model) for
+                     * the per-gene rows: the per-gene posterior table of gene_regression.py:165-174 without the trace.
+                     * With k6 set, `trace` may be NULL (no positions stored). */
 } bgh_nuts_async_buffers;
 
 int bgh_nuts_run(bgh_ctx* ctx, const bgh_nuts_async_buffers* buf, const bgh_nuts_cfg* cfg, int32_t tune,

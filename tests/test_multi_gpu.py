@@ -24,15 +24,17 @@ def test_fused_peer_exchange_matches_nccl(world):
     assert "bit-identical on all ranks: True" in out.stdout
 
 
-@pytest.mark.parametrize("world,model", [(2, "gene"), (4, "gene"), (8, "gene"), (2, "gw")])
-def test_sharded_sampler_matches_single_gpu(world, model):
-    """Gene-block sharded NUTS: every rank samples its rows of q, the per-chain sums (kinetic
-    energy, U-turn dots) are all-reduced over peer memory inside the scalar kernels; all ranks must take
-    bit-identical decisions and reproduce the single-GPU chains (tools/sharded_sampler_check.py)."""
+@pytest.mark.parametrize("world,model,driver", [(2, "gene", "persistent"), (4, "gene", "persistent"), (8, "gene", "persistent"),
+                                                (2, "gw", "persistent"), (2, "gene", "lockstep")])
+def test_sharded_sampler_matches_single_gpu(world, model, driver):
+    """Gene-block sharded NUTS: every rank samples its rows of q, the per-chain sums (likelihood sums,
+    kinetic energy, U-turn dots) travel in ONE peer exchange per leapfrog inside the persistent kernel (or, lock-step
+    driver, are all-reduced inside the scalar kernels); all ranks must take bit-identical decisions and reproduce the
+    single-GPU chains (tools/sharded_sampler_check.py)."""
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
-    env = dict(os.environ, M="60000", G="300", C="8", TUNE="12", DRAWS="6", MODEL=model, MASTER_ADDR="127.0.0.1")
+    env = dict(os.environ, M="60000", G="300", C="8", TUNE="12", DRAWS="6", MODEL=model, DRIVER=driver, MASTER_ADDR="127.0.0.1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(29560 + world), os.path.join(ROOT, "tools", "sharded_sampler_check.py")]
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)

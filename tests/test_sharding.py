@@ -13,18 +13,19 @@ import numpy as np
 import pytest
 
 from baghera_b200 import synth
-from baghera_b200.sharding import assemble_global_grad, shard_dataset
+from baghera_b200.sharding import assemble_global_grad, shard_dataset, shard_snps_only
 from oracle import model_oracle as mo
 from helpers import REL_TOL, grad_rel_err
 
 
-def _payload_and_grad_from_oracle(sh, Qloc, c, fix=False):
+def _payload_and_grad_from_oracle(sh, Qloc, c, rank, fix=False):
     """What bgh_logp_grad_local produces for one rank, restated with numpy: payload rows
-    {sum r^2/l, sum r/l, sum(beta-mi) [owned genes], sum(beta-mi)^2, shared-gene residual sums} and the
-    gradient rows of the non-shared local genes."""
+    {sum r^2/l, sum r/l, sum(beta-mi) [genes whose prior terms this rank counts], sum(beta-mi)^2, residual sums of the
+    replicated genes} and the gradient rows of the rank's own (whole) genes."""
     C = Qloc.shape[0]
     chi2, ld = sh.chi2.astype(np.float64), sh.ld.astype(np.float64)
-    payload = np.zeros((4 + sh.cfg["n_shared_rows"], C))
+    n_rep = sh.n_replicated
+    payload = np.zeros((4 + n_rep, C))
     grad = np.full((C, 3 + sh.n_genes), np.nan)
     for i in range(C):
         q = Qloc[i]
@@ -34,19 +35,14 @@ def _payload_and_grad_from_oracle(sh, Qloc, c, fix=False):
         payload[0, i] = np.sum(r * r / ld)
         payload[1, i] = np.sum(r / ld)
         owned = np.ones(sh.n_genes, bool)
-        if sh.cfg["first_gene_partial"]:
-            owned[0] = False                      # the gene's first SNP lives on a previous rank
+        owned[:n_rep] = rank == 0                 # a replicated gene's prior terms are counted by rank 0 only
         d = beta - mi
         payload[2, i] = np.sum(d[owned])
         payload[3, i] = np.sum(d[owned] ** 2)
         sums = np.bincount(sh.gene_id, weights=r, minlength=sh.n_genes)
         g = c * sums - d / W ** 2
-        if sh.cfg["first_gene_row"] >= 0:
-            payload[4 + sh.cfg["first_gene_row"], i] += sums[0]
-            g[0] = np.nan
-        if sh.cfg["last_gene_row"] >= 0 and not (sh.n_genes == 1 and sh.cfg["first_gene_row"] >= 0):
-            payload[4 + sh.cfg["last_gene_row"], i] += sums[-1]
-            g[-1] = np.nan
+        payload[4:, i] = sums[:n_rep]
+        g[:n_rep] = np.nan
         grad[i, 3:] = g
     return payload, grad
 
@@ -63,9 +59,8 @@ def _finish_from_payload(sh, Qloc, payload, grad, c, G_total, lik_const_total, f
         grad[i, 0] = 1 / W - 1 + S2 / W ** 2 - G_total
         grad[i, 1] = -(e - 1) + (0.0 if fix else A_e)
         grad[i, 2] = 1 - 2 * mi + mi * (1 - mi) * S1 / W ** 2
-        for row, gl in ((sh.cfg["first_gene_row"], 0), (sh.cfg["last_gene_row"], sh.n_genes - 1)):
-            if row >= 0:
-                grad[i, 3 + gl] = c * payload[4 + row, i] - (q[3 + gl] - mi) / W ** 2
+        for j in range(sh.n_replicated):
+            grad[i, 3 + j] = c * payload[4 + j, i] - (q[3 + j] - mi) / W ** 2
     return lp, grad
 
 
@@ -75,30 +70,31 @@ def test_shard_plan(world):
     shards = [shard_dataset(d.chi2, d.ld, d.gene_id, d.G, r, world) for r in range(world)]
     assert sum(len(s.chi2) for s in shards) == d.M
     lens = [len(s.chi2) for s in shards]
-    assert max(lens) - min(lens) <= 1                                   # balanced by SNP count
+    assert max(lens) - min(lens) <= 0.2 * d.M / world                   # whole genes, balanced by SNP count (200 genes: coarse)
+    counts = np.bincount(d.gene_id, minlength=d.G)
     for r, s in enumerate(shards):
-        assert s.gene_id.min() == 0 and s.gene_id.max() == s.n_genes - 1 and np.all(np.diff(s.gene_id) >= 0)
-        if r > 0:
-            prev = shards[r - 1]
-            assert bool(s.cfg["first_gene_partial"]) == (prev.gene_lo + prev.n_genes - 1 == s.gene_lo)
-            assert bool(prev.cfg["last_gene_partial"]) == bool(s.cfg["first_gene_partial"])
-        assert s.cfg["n_shared_rows"] == len(s.shared_genes)
-    # NonCoding (45% of SNPs, last label) must be shared once world >= 3
-    if world >= 3:
-        assert d.G - 1 in shards[-1].shared_genes
+        assert s.gene_id.min() == 0 and s.gene_id.max() == s.n_genes - 1
+        assert s.cfg["n_shared_rows"] == s.cfg["n_replicated"] == len(s.shared_genes) == s.n_replicated
+        assert s.shared_genes == shards[0].shared_genes                 # every rank holds every replicated gene
+        assert s.cfg["owns_replicated"] == int(r == 0)
+        # a non-replicated gene lives on exactly one rank, with all of its SNPs
+        own = s.gene_ids[s.n_replicated:]
+        assert np.array_equal(np.bincount(s.gene_id, minlength=s.n_genes)[s.n_replicated:], counts[own])
+    # NonCoding (45% of SNPs, last label) is replicated
+    assert d.G - 1 in shards[-1].shared_genes
+    allg = np.concatenate([s.gene_ids[s.n_replicated:] for s in shards] + [np.asarray(shards[0].shared_genes, dtype=np.int64)])
+    assert np.array_equal(np.sort(allg), np.arange(d.G))
 
 
 @pytest.mark.parametrize("world", [2, 3, 5, 8])
 def test_every_global_row_is_owned_once(world):
-    """Sharded sampler: the per-chain sums are all-reduced over ranks, so every global coordinate must be
-    counted by exactly one rank (replicated head rows and rank-spanning genes included)."""
+    """Sharded sampler: the per-chain sums are exchanged between ranks, so every global coordinate must be counted by
+    exactly one rank (replicated head rows and replicated genes included)."""
     d = synth.make_arrays(20_000, 200)
     shards = [shard_dataset(d.chi2, d.ld, d.gene_id, d.G, r, world) for r in range(world)]
     count = np.zeros(3 + d.G, dtype=int)
     for r, sh in enumerate(shards):
-        own = sh.owned_rows(r)
-        count[:3] += own[:3]
-        count[3 + sh.gene_lo: 3 + sh.gene_lo + sh.n_genes] += own[3:]
+        np.add.at(count, sh.row_coords(), sh.owned_rows(r).astype(int))
     assert np.all(count == 1), np.flatnonzero(count != 1)
 
 
@@ -114,7 +110,7 @@ def _gloo_worker(rank, world, port, q):
         Q = synth.jittered_start(d.G + 3, C, seed=4)
         sh = shard_dataset(d.chi2, d.ld, d.gene_id, d.G, rank, world)
         Qloc = sh.local_q(Q)
-        payload, grad = _payload_and_grad_from_oracle(sh, Qloc, d.c)
+        payload, grad = _payload_and_grad_from_oracle(sh, Qloc, d.c, rank)
         t = torch.from_numpy(payload)
         dist.all_reduce(t)                                            # the per-step exchange
         const = torch.tensor([mo.lik_const(sh.ld.astype(np.float64))], dtype=torch.float64)
@@ -198,6 +194,78 @@ def test_emulated_ranks_on_one_gpu(world, M, G):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("world,M,G,model", [(2, 20_000, 200, "gene"), (4, 60_000, 300, "gene"), (8, 1_100_000, 15_000, "gene"),
+                                             (3, 30_000, 100, "gamma"), (4, 400_000, 1, "gw")])
+def test_fused_exchange_kernel_with_ranks_emulated_on_one_gpu(world, M, G, model):
+    """The kernel that ships for N > 1 (bgh_logp_grad_sharded: likelihood pass | grid barrier | per-chain closing with the
+    LL-protocol peer exchange) against the oracle on ONE GPU: the ranks' contexts are connected in-process and run one
+    after the other — first every rank deposits its payload in the peers' mailboxes without waiting (send-only), then
+    every rank runs normally with the same mailbox sequence number and finds the peers' data waiting."""
+    import torch
+    from baghera_b200.engine import Engine
+    d = synth.make_arrays(M, G)
+    C = 64 if M > 300_000 and model == "gene" else 8
+    gw, gamma = model == "gw", model == "gamma"
+    D = 2 if gw else (d.G + 2 if gamma else d.G + 3)
+    head = 2 if (gw or gamma) else 3
+    c = d.n_patients if gamma else d.c
+    Q = synth.jittered_start(D, C, seed=6, model=model)
+    if gw:
+        shards = [shard_snps_only(d.chi2, d.ld, r, world) for r in range(world)]
+    else:
+        shards = [shard_dataset(d.chi2, d.ld, d.gene_id, d.G, r, world) for r in range(world)]
+    engines = [Engine(s.chi2, s.ld, None if gw else s.gene_id, s.n_genes, c, C, model=model, shard=s.cfg,
+                      gamma_rate=d.N_1kG if gamma else None) for s in shards]
+    const = sum(e.lik_const for e in engines)
+    for e in engines:
+        e.set_lik_const(const)
+        e.peer_export()
+    for r, e in enumerate(engines):
+        e.peer_connect_local(r, engines)
+    Cp = engines[0].Cp
+    qs = [e.to_device_layout(Q if gw else s.local_q(Q, head)) for e, s in zip(engines, shards)]
+    grads = [torch.zeros_like(q) for q in qs]
+    lps = [torch.zeros(Cp, dtype=torch.float64, device="cuda") for _ in engines]
+    for seq in range(2):                                              # twice: the mailbox parities / tags advance
+        for e, q, g, lp in zip(engines, qs, grads, lps):
+            e.debug_peer_mode(True, seq)
+            e.logp_grad_sharded(q, lp, g)
+        torch.cuda.synchronize()
+        for e, q, g, lp in zip(engines, qs, grads, lps):
+            e.debug_peer_mode(False, seq)
+            e.logp_grad_sharded(q, lp, g)
+        torch.cuda.synchronize()
+        assert all(e.peer_status() == 0 for e in engines)
+    n_ref = min(C, 2 if M > 300_000 and not gw else 8)
+    chi2, ld = d.chi2.astype(np.float64), d.ld.astype(np.float64)
+    if gw:
+        ref = [mo.gw_logp_grad_closed(Q[i], chi2, ld, d.c) for i in range(n_ref)]
+    elif gamma:
+        ref = [mo.gamma_logp_grad_closed(Q[i], chi2, ld, d.gene_id.astype(np.int64), float(d.n_patients), float(d.N_1kG)) for i in range(n_ref)]
+    else:
+        lp_ref, g_ref = mo.batch_closed(Q[:n_ref], chi2, ld, d.gene_id.astype(np.int64), d.c)
+        ref = list(zip(lp_ref, g_ref))
+    g_loc = [e.from_device_layout(g).cpu().numpy() for e, g in zip(engines, grads)]
+    g_all = Q * np.nan if gw else assemble_global_grad(g_loc, shards, D, head)
+    for lp in lps[1:]:
+        assert torch.equal(lp[:C], lps[0][:C]), "logp differs between ranks (rank-ordered sums must be bit-identical)"
+    for i in range(n_ref):
+        assert abs(lps[0][i].item() - ref[i][0]) <= REL_TOL * abs(ref[i][0])
+        if gw:
+            for gl in g_loc:
+                assert grad_rel_err(gl[i], ref[i][1]) <= REL_TOL
+        else:
+            assert grad_rel_err(g_all[i], ref[i][1]) <= REL_TOL
+    # replicated rows carry the same gradient on every rank
+    nrep = shards[0].n_replicated
+    if not gw:
+        for gl in g_loc[1:]:
+            assert np.array_equal(gl[:, :head + nrep], g_loc[0][:, :head + nrep])
+    for e in engines:
+        e.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("world", [2, 8])
 def test_gw_model_emulated_ranks(world):
     """cfg5 shape (genome-wide model, ref: heritability.py:44-55) sharded by SNP ranges: the single slope's
@@ -207,8 +275,7 @@ def test_gw_model_emulated_ranks(world):
     d = synth.make_arrays(400_000, 1)
     C = 8
     Q = synth.jittered_start(2, C, seed=9, model="gw")
-    gid = np.zeros(d.M, dtype=np.int32)
-    shards = [shard_dataset(d.chi2, d.ld, gid, 1, r, world) for r in range(world)]
+    shards = [shard_snps_only(d.chi2, d.ld, r, world) for r in range(world)]
     engines = [Engine(s.chi2, s.ld, None, 1, d.c, C, model="gw", shard=s.cfg) for s in shards]
     Cp, rows = engines[0].Cp, engines[0].payload_rows
     assert rows == 5

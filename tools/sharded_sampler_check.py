@@ -1,6 +1,7 @@
 """torchrun --nproc-per-node N tools/sharded_sampler_check.py : the gene-block sharded NUTS sampler (every rank
-owns its rows of q; per-chain sums all-reduced over peer memory inside the scalar kernels) against the
-single-GPU sampler run with the same seed on rank 0."""
+owns its rows of q; one LL-protocol peer exchange of the per-chain sums per leapfrog inside the persistent kernel,
+DRIVER=persistent, or the lock-step transition kernels, DRIVER=lockstep) against the single-GPU lock-step sampler
+run with the same seed on rank 0."""
 import os, sys, time
 import numpy as np, torch
 import torch.distributed as dist
@@ -8,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from baghera_b200 import synth
 from baghera_b200.engine import Engine
 from baghera_b200.sampler import NutsSampler
-from baghera_b200.sharding import shard_dataset, connect_peers
+from baghera_b200.sharding import shard_dataset, shard_snps_only, connect_peers
 
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
@@ -21,18 +22,21 @@ gw = model == "gw"
 d = synth.make_arrays(M, G)
 D = 2 if gw else G + 3
 Q0 = synth.jittered_start(D, C, seed=2, model=model)
-gid = np.zeros(M, np.int32) if gw else d.gene_id
-sh = shard_dataset(d.chi2, d.ld, gid, G, rank, world)
+driver = os.environ.get("DRIVER", "persistent")
+sh = shard_snps_only(d.chi2, d.ld, rank, world) if gw else shard_dataset(d.chi2, d.ld, d.gene_id, G, rank, world)
 eng = Engine(sh.chi2, sh.ld, None if gw else sh.gene_id, sh.n_genes, d.c, C, model=model, device=lr, shard=sh.cfg)
 lc = torch.tensor([eng.lik_const], dtype=torch.float64, device=dev)
 dist.all_reduce(lc)
 eng.set_lik_const(float(lc.item()))
 connect_peers(eng, dist, dev)
-s = NutsSampler(eng, seed=11, gene_lo=0 if gw else sh.gene_lo, n_dim_total=D)
+s = NutsSampler(eng, seed=11, row_coords=None if gw else sh.row_coords(), n_dim_total=D)
 s.init(Q0 if gw else sh.local_q(Q0))
+dist.barrier()
 t0 = time.perf_counter()
-out = s.sample_lockstep(DRAWS, TUNE)
+out = s.sample_lockstep(DRAWS, TUNE) if driver == "lockstep" else s.sample(DRAWS, TUNE)
 secs = time.perf_counter() - t0
+if driver != "lockstep":
+    out["leapfrogs"] = out["stats"][:, 2].sum(axis=1)        # per-transition tree sizes summed over chains
 assert eng.peer_status() == 0, eng.peer_status()
 st = torch.as_tensor(out["stats"], device=dev)
 allst = [torch.empty_like(st) for _ in range(world)]
@@ -41,18 +45,18 @@ same = all(torch.equal(allst[0], x) for x in allst)            # every rank took
 tr = out["trace"].cpu().numpy()                                 # [draws, D_local, C]
 ok = True
 if rank == 0:
-    print("sharded x%d: %d transitions, %d leapfrogs, %.2f s; stats bit-identical on all ranks: %s"
-          % (world, TUNE + DRAWS, int(out["leapfrogs"].sum()), secs, same), flush=True)
+    print("sharded x%d (%s): %d transitions, %d leapfrogs%s, %.2f s; stats bit-identical on all ranks: %s"
+          % (world, driver, TUNE + DRAWS, int(out["leapfrogs"].sum()), (", %d ticks = %.1f us/tick" % (out["ticks"], secs / out["ticks"] * 1e6))
+             if driver != "lockstep" else "", secs, same), flush=True)
 gathered = [None] * world
-dist.all_gather_object(gathered, (sh.gene_lo, sh.n_genes, tr))
+dist.all_gather_object(gathered, (sh.row_coords(2 if gw else 3), tr))
 if rank == 0:
     full = np.full((DRAWS, D, C), np.nan)
-    for lo, ng, t in gathered:
+    for rc, t in gathered:
         if gw:
             full[:] = t
         else:
-            full[:, :3] = t[:, :3]
-            full[:, 3 + lo:3 + lo + ng] = t[:, 3:]
+            full[:, rc] = t
     e1 = Engine(d.chi2, d.ld, None if gw else d.gene_id, G, d.c, C, model=model, device=lr)
     s1 = NutsSampler(e1, seed=11)
     s1.init(Q0)
