@@ -106,33 +106,47 @@ __device__ __forceinline__ ChainConst chain_const(const FinParams& p, int ch)
     return c;
 }
 
-__device__ __forceinline__ void finish_chain(const FinParams& p, int ch, const ChainSums& s, const ChainConst& c)
+// logp and the gradients of the head rows of one chain (g[0..2]; the genome-wide model's g[1] comes from finish_gene)
+__device__ __forceinline__ void chain_closing(const FinParams& p, int ch, const ChainSums& s, const ChainConst& c, double& logp, double (&g)[3])
 {
-    const int Cp = p.Cp;
+    g[0] = g[1] = g[2] = 0.0;
     if (p.model == BGH_MODEL_GENE_GAMMA) {
         // S1 = sum_g x_g, S2 = sum_g beta_g (owned genes)
         const double e = p.q[0 * p.ds + ch * p.cs];
-        p.logp[ch] = c.lp0 + c.mi * s.S1 - p.gamma_rate * s.S2 - 0.5 * s.A_ll;
-        p.grad[0 * p.ds + ch * p.cs] = -kGammaETau * (e - 1.0) + (p.fix ? 0.0 : s.A_e);
-        p.grad[1 * p.ds + ch * p.cs] = 1.0 - 2.0 * c.mi + c.mi * (1.0 - c.mi) * (c.iW + s.S1);
+        logp = c.lp0 + c.mi * s.S1 - p.gamma_rate * s.S2 - 0.5 * s.A_ll;
+        g[0] = -kGammaETau * (e - 1.0) + (p.fix ? 0.0 : s.A_e);
+        g[1] = 1.0 - 2.0 * c.mi + c.mi * (1.0 - c.mi) * (c.iW + s.S1);
         return;
     }
     if (p.model == BGH_MODEL_GENE_NORMAL) {
         const double e = p.q[1 * p.ds + ch * p.cs];
         const double G = (double)p.G_total;
-        p.logp[ch] = c.lp0 - 0.5 * s.S2 * c.iW2 - 0.5 * s.A_ll;
-        p.grad[0 * p.ds + ch * p.cs] = c.iW - 1.0 + s.S2 * c.iW2 - G;
-        p.grad[1 * p.ds + ch * p.cs] = -(e - 1.0) + (p.fix ? 0.0 : s.A_e);
-        p.grad[2 * p.ds + ch * p.cs] = 1.0 - 2.0 * c.mi + c.mi * (1.0 - c.mi) * s.S1 * c.iW2;
+        logp = c.lp0 - 0.5 * s.S2 * c.iW2 - 0.5 * s.A_ll;
+        g[0] = c.iW - 1.0 + s.S2 * c.iW2 - G;
+        g[1] = -(e - 1.0) + (p.fix ? 0.0 : s.A_e);
+        g[2] = 1.0 - 2.0 * c.mi + c.mi * (1.0 - c.mi) * s.S1 * c.iW2;
     } else {
         const double x0 = p.q[0 * p.ds + ch * p.cs];
-        p.logp[ch] = c.lp0 - 0.5 * s.A_ll;
+        logp = c.lp0 - 0.5 * s.A_ll;
         if (p.fix) {
             const double sg = c.iW;
-            p.grad[0 * p.ds + ch * p.cs] = s.A_e * (kGwFixHi - kGwFixLo) * sg * (1.0 - sg) + (1.0 - 2.0 * sg);
+            g[0] = s.A_e * (kGwFixHi - kGwFixLo) * sg * (1.0 - sg) + (1.0 - 2.0 * sg);
         } else {
-            p.grad[0 * p.ds + ch * p.cs] = -(x0 - 1.0) + s.A_e;
+            g[0] = -(x0 - 1.0) + s.A_e;
         }
+    }
+}
+
+__device__ __forceinline__ void finish_chain(const FinParams& p, int ch, const ChainSums& s, const ChainConst& c)
+{
+    double lp, g[3];
+    chain_closing(p, ch, s, c, lp, g);
+    p.logp[ch] = lp;
+    p.grad[0 * p.ds + ch * p.cs] = g[0];
+    if (p.model == BGH_MODEL_GENE_GAMMA) p.grad[1 * p.ds + ch * p.cs] = g[1];
+    if (p.model == BGH_MODEL_GENE_NORMAL) {
+        p.grad[1 * p.ds + ch * p.cs] = g[1];
+        p.grad[2 * p.ds + ch * p.cs] = g[2];
     }
 }
 
@@ -153,17 +167,19 @@ __device__ __forceinline__ GeneCoef load_gene_coef(const FinParams& p, int gene,
     }
     return gc;
 }
+// gradient of a gene's row (genome-wide model: of the slope row 1) from its total residual sum
+__device__ __forceinline__ double gene_grad(const FinParams& p, double sum_r, const GeneCoef& gc)
+{
+    if (p.model == BGH_MODEL_GENE_GAMMA) return fma(gc.beta, fma(p.c, sum_r, -p.gamma_rate), gc.mi);
+    if (p.model == BGH_MODEL_GENE_NORMAL) return fma(p.c, sum_r, -(gc.beta - gc.mi) * gc.iW2);
+    return p.c * sum_r * gc.mi * (1.0 - gc.mi) + 1.0 - 3.0 * gc.mi;      // (c*sum_r - 1/(1-mi)) * mi(1-mi) + (1 - 2mi)
+}
 __device__ __forceinline__ void finish_gene(const FinParams& p, int gene, int ch, double sum_r, const GeneCoef& gc)
 {
-    const int Cp = p.Cp;
-    if (p.model == BGH_MODEL_GENE_GAMMA) {
-        p.grad[(long long)(2 + gene) * p.ds + ch * p.cs] = fma(gc.beta, fma(p.c, sum_r, -p.gamma_rate), gc.mi);
-    } else if (p.model == BGH_MODEL_GENE_NORMAL) {
-        p.grad[(long long)(3 + gene) * p.ds + ch * p.cs] = fma(p.c, sum_r, -(gc.beta - gc.mi) * gc.iW2);
-    } else {
-        // (c*sum_r - 1/(1-mi)) * mi(1-mi) + (1 - 2mi)
-        p.grad[1 * p.ds + ch * p.cs] = p.c * sum_r * gc.mi * (1.0 - gc.mi) + 1.0 - 3.0 * gc.mi;
-    }
+    const double g = gene_grad(p, sum_r, gc);
+    if (p.model == BGH_MODEL_GENE_GAMMA) p.grad[(long long)(2 + gene) * p.ds + ch * p.cs] = g;
+    else if (p.model == BGH_MODEL_GENE_NORMAL) p.grad[(long long)(3 + gene) * p.ds + ch * p.cs] = g;
+    else p.grad[1 * p.ds + ch * p.cs] = g;
 }
 
 }  // namespace bgh

@@ -57,7 +57,8 @@ constexpr size_t kT2CmdBytes = kT2MaxChains * (sizeof(double) + sizeof(int));
 constexpr size_t kT2Kin0Offset = kT2CmdOffset + kT2CmdBytes;                  // double[kT2MaxChains] + int[kT2MaxChains]
 constexpr int kT2MaxRowsSmem = 8192;
 constexpr size_t kT2RowsOffset = kT2Kin0Offset + kT2MaxChains * (sizeof(double) + sizeof(int));   // int[kT2MaxRowsSmem]
-constexpr size_t kT2SmemBytes = kT2RowsOffset + kT2MaxRowsSmem * sizeof(int);
+constexpr size_t kT2LateOffset = kT2RowsOffset + kT2MaxRowsSmem * sizeof(int);   // int[kLikThreads] late-row table
+constexpr size_t kT2SmemBytes = kT2LateOffset + kLikThreads * sizeof(int);
 static_assert(kT2SmemBytes <= 227 * 1024, "shared memory of the fused sampler kernel");
 
 size_t tick2_smem_bytes() { return kT2SmemBytes; }
@@ -209,8 +210,8 @@ __device__ __forceinline__ void row_half_step(const NutsParams& p, int bits, dou
 // second half of the leapfrog for one row whose new gradient is known.  acc[j * stride] accumulates quantity j
 // (kAq* numbering of bgh_sampler.h) of the row's chain; the kinetic energy (quantity 0) stays in a register.
 // ck0 = checkpoint of the first checked level, tot = running momentum total (both loaded by the caller).
-__device__ __forceinline__ void row_finish(const NutsParams& p, int bits, double h, size_t i, size_t wo, double gnew, double ph, double var,
-                                           double tot, double2 ck0, double& kin, double* acc, int stride, unsigned long long pol)
+__device__ __forceinline__ double row_finish(const NutsParams& p, int bits, double h, size_t i, size_t wo, double gnew, double ph, double var,
+                                             double tot, double2 ck0, double& kin, double* acc, int stride, unsigned long long pol)
 {
     const size_t vec = (size_t)p.D * p.Cp;
     const double mom = fma(h, gnew, ph);
@@ -235,6 +236,7 @@ __device__ __forceinline__ void row_finish(const NutsParams& p, int bits, double
         acc[kAqTree0 * stride] = fma(ps, vel, acc[kAqTree0 * stride]);
         acc[(kAqTree0 + 1) * stride] = fma(ps, var * po, acc[(kAqTree0 + 1) * stride]);
     }
+    return mom;
 }
 
 // which of the kAsyncPartials per-chain quantities a chain running under command `bits` produces this tick
@@ -536,6 +538,29 @@ __device__ __forceinline__ T2Scalar t2_scalar_smem(unsigned char* smem_raw)
 static_assert((32 * 16 + kT2MaxPay + 32 + 16 + kLikWarps + kLikWarps * kAsyncPartials + kMaxPeers * kT2MaxPay + 2 + kT2MaxSplit) * sizeof(double) <=
                   kLikStageBytes, "scalar phase shared memory");
 
+// residual sums of the split genes of chain c in fin_phase's summation order (bit-identical to the evaluation kernels):
+// short lists (<= kShortSplit slots) one THREAD per gene, sequentially in list order — all genes in flight at once, three
+// dependent loads deep; long lists (NonCoding) one warp per gene: 16 strided sequential sums added in order.
+__device__ __forceinline__ void split_gene_sums(const FinParams& f, int c, double* s_sr)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Cp = f.Cp;
+    for (int k = f.n_long + tid; k < f.n_split; k += blockDim.x) {
+        const int s0 = f.split_ptr[k], n = f.split_ptr[k + 1] - s0;
+        double tot = 0.0;
+        for (int i = 0; i < n; ++i) tot += f.slots[(size_t)f.split_slots[s0 + i] * Cp + c];
+        s_sr[k] = tot;
+    }
+    for (int k = warp; k < f.n_long; k += kLikWarps) {
+        const int s0 = f.split_ptr[k], n = f.split_ptr[k + 1] - s0;
+        double acc = 0.0, tot = 0.0;
+        if (lane < kLikWarps)
+            for (int i = lane; i < n; i += kLikWarps) acc += f.slots[(size_t)f.split_slots[s0 + i] * Cp + c];
+        for (int w = 0; w < kLikWarps; ++w) tot += __shfl_sync(0xffffffffu, acc, w);
+        if (lane == 0) s_sr[k] = tot;
+    }
+}
+
 // late rows of chain c: local index r in [0, n_late): head rows first, then the split genes in list order
 __device__ __forceinline__ int t2_n_late(const Tick2Params& t)
 {
@@ -577,12 +602,22 @@ __device__ __forceinline__ void t2_late_finish(const Tick2Params& t, const T2Sca
     }
     acc[0] = kin;
     const unsigned used = used_quantities(bits) & ~(1u << kAqKin0);
-    // fixed-order CTA sums of the quantities this chain uses
+    // fixed-order CTA sums of the quantities this chain uses: xor tree inside the warp, then the warps in order
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll 1
     for (int j = 0; j < kAsyncPartials; ++j) {
-        if (!((used >> j) & 1u)) continue;                                 // CTA-uniform
-        const double tot = cta_sum(acc[j], s.red);
-        if (threadIdx.x == 0) s.sum[kT2Lik + j] += tot;
+        if (!((used >> j) & 1u)) continue;
+        double x = acc[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) s.red2[warp * kAsyncPartials + j] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < kAsyncPartials && ((used >> threadIdx.x) & 1u)) {
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < kLikWarps; ++w) tot += s.red2[w * kAsyncPartials + threadIdx.x];
+        s.sum[kT2Lik + threadIdx.x] += tot;
     }
     __syncthreads();
 }
@@ -657,7 +692,7 @@ __device__ __forceinline__ void tick2_prologue(const Tick2Params& t, unsigned ch
     }
 }
 
-__device__ __forceinline__ void tick2_scalar(const Tick2Params& t, unsigned char* smem_raw, unsigned tick_global, unsigned long long* tr)
+__device__ __noinline__ void tick2_scalar_generic(const Tick2Params& t, unsigned char* smem_raw, unsigned tick_global, unsigned long long* tr)
 {
     const AsyncParams& a = t.a;
     const NutsParams& p = a.n;
@@ -699,22 +734,7 @@ __device__ __forceinline__ void tick2_scalar(const Tick2Params& t, unsigned char
                 if (lane == 0) s.sum[k] = acc;
             }
         }
-        // residual sums of the split genes, one warp per gene, in fin_phase's summation order: long lists (> kShortSplit
-        // slots) as 16 strided sequential sums added in order, short lists sequentially
-        for (int k = warp; k < f.n_split; k += kLikWarps) {
-            const int s0 = f.split_ptr[k], n = f.split_ptr[k + 1] - s0;
-            double tot = 0.0;
-            if (k < f.n_long) {
-                double acc = 0.0;
-                if (lane < kLikWarps)
-                    for (int i = lane; i < n; i += kLikWarps) acc += f.slots[(size_t)f.split_slots[s0 + i] * p.Cp + c];
-                for (int w = 0; w < kLikWarps; ++w) tot += __shfl_sync(0xffffffffu, acc, w);
-            } else {
-                const double x = lane < n ? f.slots[(size_t)f.split_slots[s0 + lane] * p.Cp + c] : 0.0;
-                for (int i = 0; i < n; ++i) tot += __shfl_sync(0xffffffffu, x, i);
-            }
-            if (lane == 0) s.sr[k] = tot;
-        }
+        split_gene_sums(f, c, s.sr);
         __syncthreads();
         if (tr) tr[5] = global_timer_ns();
         int phase = s.fl[kAfPhase];
@@ -955,6 +975,365 @@ __device__ __forceinline__ void tick2_scalar(const Tick2Params& t, unsigned char
 }
 
 // ---------------------------------------------------------------------------------------------
+// Scalar phase, latency-optimised path (at most one late row per thread, i.e. n_late <= 512 — always, unless hundreds of
+// genes are larger than an SNP range).  Same arithmetic and summation orders as tick2_scalar_generic; what differs is that
+// nothing waits for a global round trip it does not need: the tick's command comes from the CTA's shared-memory copy, every
+// thread fetches the state of "its" late row while the partial sums are being reduced, gradients and logp travel through
+// shared memory instead of global memory, and a late row that simply continues its trajectory starts the next half step
+// from registers.
+// s_lrow: late-row table (persistent shared memory): local row | replicated << 30.
+// ---------------------------------------------------------------------------------------------
+constexpr int kLateRep = 1 << 30;
+
+__device__ __forceinline__ void tick2_scalar(const Tick2Params& t, unsigned char* smem_raw, unsigned tick_global, unsigned long long* tr,
+                                             const int* s_bits, const double* s_h, const int* s_lrow, int n_late)
+{
+    const AsyncParams& a = t.a;
+    const NutsParams& p = a.n;
+    const FinParams& f = t.fin;
+    const T2Scalar s = t2_scalar_smem(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_blk = (int)gridDim.x;
+    const bool single = t.peer.world <= 1;
+    const bool gw = t.lik.model == BGH_MODEL_GW_NORMAL;
+    const size_t vec = (size_t)p.D * p.Cp;
+    const unsigned long long pol = l2_keep_policy();
+    for (int c = blockIdx.x; c < p.C; c += n_blk) {
+        const int bits_old = s_bits[c];                  // the command this tick's vector work ran under
+        const double h_old = s_h[c];
+        const bool run = (bits_old & kCbRun) != 0;
+        const size_t wo = (bits_old & kCbW) ? (size_t)kXStride * vec : 0;
+        const unsigned used = used_quantities(bits_old);
+        const int nl = (bits_old >> kCbNLvlShift) & 15, lm = (bits_old >> kCbLvlMinShift) & 15;
+        // ---- A: everything this phase reads from global memory is requested now
+        if (tid < kAscCount) s.sc[tid] = sc(p, tid, c);
+        if (tid >= 32 && tid < 32 + kAfCount) s.fl[tid - 32] = t2_afl(a, tid - 32, c);
+        const bool has_row = tid < n_late;
+        const int lr = has_row ? s_lrow[tid] : 0;
+        const int d = lr & (kLateRep - 1);
+        const bool rep_row = single || (lr & kLateRep) != 0;           // its gradient needs the exchanged totals
+        const size_t i = (size_t)d * p.Cp + c;
+        double qv = 0.0, pw = 0.0, var = 0.0, tot = 0.0;
+        double2 ck0 = make_double2(0.0, 0.0);
+        if (has_row && run) {
+            qv = ldk(p.state + (size_t)kSlotQL * vec + wo + i, pol);
+            pw = ldk(p.state + (size_t)kSlotPL * vec + wo + i, pol);
+            var = ldk(p.state + (size_t)kSlotVar * vec + i, pol);
+            tot = ldk(p.state + (size_t)kSlotT * vec + i, pol);
+            if (nl > 0) ck0 = *t2_ckpt(p, lm, i);
+            for (int l = 1; l < nl; ++l) prefetch_l1(t2_ckpt(p, lm + l, i));     // deep checks: every level in flight now
+            if (bits_old & kCbLast) prefetch_l1(p.state + (size_t)kSlotPL * vec + (wo ? 0 : (size_t)kXStride * vec) + i);
+        }
+        FinParams fc = f;                                // closing formulas: the chain's working buffer
+        fc.q = f.q + wo;
+        fc.grad = f.grad + wo;
+        const ChainConst cc = chain_const(fc, c);        // every thread: cheap, avoids a broadcast
+        GeneCoef gc;
+        gc.iW2 = gc.mi = gc.beta = 0.0;
+        const int k_split = (!gw && d >= t.row0) ? tid - t.row0 : (gw && tid == 1 ? 0 : -1);     // split-gene index of this thread's row
+        if (has_row && k_split >= 0) gc = load_gene_coef(fc, f.split_gene[k_split], c, true);
+        // likelihood sums in fin_phase's order (bit-identical logp / head gradients); sampler sums lane-strided + xor tree
+        for (int k = warp; k < kT2Nq; k += kLikWarps) {
+            const bool lik = k < kT2Lik;
+            if (!lik && !((used >> (k - kT2Lik)) & 1u)) {
+                if (lane == 0) s.sum[k] = 0.0;
+                continue;
+            }
+            const double* const src = lik ? t.lik.part + (size_t)k * p.Cp + c : t.part + (size_t)(k - kT2Lik) * p.Cp + c;
+            const size_t stride = (size_t)(lik ? kT2Lik : kAsyncPartials) * p.Cp;
+            double acc = 0.0;
+            for (int i0 = 0; i0 * 32 < f.n_cta; i0 += 8) {
+                double v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int row = lane + 32 * (i0 + j);
+                    v[j] = row < f.n_cta ? src[(size_t)row * stride] : 0.0;
+                }
+                acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) s.sum[k] = acc;
+        }
+        split_gene_sums(f, c, s.sr);
+        __syncthreads();
+        if (tr) tr[5] = global_timer_ns();
+        if (tid == 0) s.sum[kT2Lik + kAqKin0] += s.sc[kScKin0LateLocal];   // fresh momenta of the late rows (refreshed last tick)
+
+        double kin = 0.0, gnew = 0.0, mom_new = pw;
+        double acc[kAsyncPartials];
+#pragma unroll 1
+        for (int j = 0; j < kAsyncPartials; ++j) acc[j] = 0.0;
+        // fixed-order CTA sum of the used quantities of acc[] into s.sum (xor tree inside the warp, then the warps in order)
+        auto reduce_acc = [&]() {
+            acc[0] = kin;
+            const unsigned u = used & ~(1u << kAqKin0);
+#pragma unroll 1
+            for (int j = 0; j < kAsyncPartials; ++j) {
+                if (!((u >> j) & 1u)) continue;
+                double x = acc[j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                if (lane == 0) s.red2[warp * kAsyncPartials + j] = x;
+            }
+            __syncthreads();
+            if (tid < kAsyncPartials && ((u >> tid) & 1u)) {
+                double tsum = 0.0;
+#pragma unroll
+                for (int w = 0; w < kLikWarps; ++w) tsum += s.red2[w * kAsyncPartials + tid];
+                s.sum[kT2Lik + tid] += tsum;
+            }
+            __syncthreads();
+            kin = 0.0;
+#pragma unroll 1
+            for (int j = 0; j < kAsyncPartials; ++j) acc[j] = 0.0;
+        };
+        if (!single) {
+            // ---- B: rank-local late rows (their residual sums are complete on this rank), then the exchange
+            if (has_row && !rep_row) {
+                gnew = gene_grad(fc, s.sr[k_split], gc);
+                stk(p.state + (size_t)kSlotGL * vec + wo + i, gnew, pol);
+                if (run) mom_new = row_finish(p, bits_old, h_old, i, wo, gnew, pw, var, tot, ck0, kin, acc, 1, pol);
+            }
+            if (run) reduce_acc();
+            // payload = the chain's sums followed by the residual sums of the replicated genes (payload row 4 + j)
+            for (int k = tid; k < f.n_split; k += blockDim.x)
+                if (f.split_row[k] >= 0) s.pay[kT2Nq + f.split_row[k]] = s.sr[k];
+            __syncthreads();
+            if (tr) tr[11] = global_timer_ns();
+            t2_exchange(t.peer, p.Cp, c, tick_global, s.pay, s.tmp, t.status);
+            if (tr) tr[12] = global_timer_ns();
+            for (int k = tid; k < f.n_split; k += blockDim.x)
+                if (f.split_row[k] >= 0) s.sr[k] = s.pay[kT2Nq + f.split_row[k]];
+            __syncthreads();
+        }
+        // ---- C: closing formulas (logp, gradient of the head rows) through shared memory
+        double* const s_hg = s.red;                      // [0..2] head gradients, [3] logp (s.red is free here)
+        if (tid == 0) {
+            s.sum[kT2Lik + kAqKin0] += s.sc[kScKin0LateRep];
+            ChainSums cs;
+            cs.A_ll = s.sum[0]; cs.A_e = s.sum[1]; cs.S1 = s.sum[2]; cs.S2 = s.sum[3];
+            double lp, g[3];
+            chain_closing(fc, c, cs, cc, lp, g);
+            f.logp[c] = lp;
+            s_hg[0] = g[0]; s_hg[1] = g[1]; s_hg[2] = g[2]; s_hg[3] = lp;
+        }
+        __syncthreads();
+        if (!run) {                                                       // CTA-uniform: finished or flushing chain
+            if (has_row && rep_row) {
+                const double g = k_split >= 0 ? gene_grad(fc, s.sr[k_split], gc) : s_hg[d];
+                stk(p.state + (size_t)kSlotGL * vec + wo + i, g, pol);
+            }
+            if (bits_old & kCbFlush) {
+                if (tid == 0) {
+                    s.fl[kAfPhase] = kPhaseFinished;
+                    s.fl[kAfMerge] = 0; s.fl[kAfTake] = 0; s.fl[kAfTakeTop] = 0; s.fl[kAfRecSlot] = -1;
+                    atomicAdd(a.n_finished, 1);
+                }
+                __syncthreads();
+                t2_store_chain(t, s, c, 0);
+            }
+            __syncthreads();
+            continue;
+        }
+        // ---- D: second half of the leapfrog for the late rows (all of them on a single rank, the replicated ones when sharded)
+        if (has_row && rep_row) {
+            gnew = k_split >= 0 ? gene_grad(fc, s.sr[k_split], gc) : s_hg[d];
+            stk(p.state + (size_t)kSlotGL * vec + wo + i, gnew, pol);
+            mom_new = row_finish(p, bits_old, h_old, i, wo, gnew, pw, var, tot, ck0, kin, acc, 1, pol);
+        }
+        const double logp_now = s_hg[3];
+        reduce_acc();
+        if (tr) tr[6] = global_timer_ns();
+
+        // ---- E: the per-chain NUTS state machine (same logic as nuts_leaf_scalar / top1 / top2 / finish kernels)
+        if (tid == 0) {
+            int phase = kPhaseRun;
+            const double* const ssum = s.sum + kT2Lik;
+            double* const s_sc = s.sc;
+            int* const s_fl = s.fl;
+            long long draw = s_fl[kAfDraw];
+            int depth = s_fl[kAfDepth], leaf = s_fl[kAfLeaf], dir = s_fl[kAfDir];
+            if (s_fl[kAfNew]) {      // the transition began this tick
+                const double e0 = ssum[kAqKin0] - s_sc[kScLogpProp];
+                s_sc[kScE0] = e0;
+                s_sc[kScEnergyProp] = e0;
+                s_sc[kScLogSizeTree] = 0.0;
+                s_sc[kScAcceptSum] = 0.0;
+                s_sc[kScNProp] = 0.0;
+                s_sc[kScMaxDE] = 0.0;
+                s_fl[kAfDiverging] = 0;
+                s_fl[kAfTurning] = 0;
+                if (!isfinite(e0)) s_fl[kAfBadStart] = 1;
+            }
+            s_fl[kAfNew] = 0; s_fl[kAfFirst] = 0; s_fl[kAfMerge] = 0; s_fl[kAfTakeTop] = 0;
+            s_fl[kAfTake] = 0; s_fl[kAfAdapt] = 0; s_fl[kAfSwitch] = 0; s_fl[kAfRecSlot] = -1; s_fl[kAfFlip] = 0;
+
+            const double kin_tot = ssum[0];
+            const double logp = logp_now;
+            const double energy = kin_tot - logp;
+            double dE = energy - s_sc[kScE0];
+            if (isnan(dE)) dE = INFINITY;
+            if (fabs(dE) > fabs(s_sc[kScMaxDE])) s_sc[kScMaxDE] = dE;
+            s_sc[kScNProp] += 1.0;
+            bool valid = true;
+            if (fabs(dE) < p.emax) {
+                s_sc[kScAcceptSum] += fmin(1.0, exp(-dE));
+                const double lw = -dE;
+                bool take;
+                if (leaf == 0) {
+                    take = true;
+                    s_sc[kScLogSizeSub] = lw;
+                } else {
+                    const double ls = logaddexp_d(s_sc[kScLogSizeSub], lw);
+                    const double u = t2_chain_uniform(p, c, draw, kPurposeLeaf, ((unsigned)depth << 16) | (unsigned)leaf);
+                    take = log(u) < lw - ls;
+                    s_sc[kScLogSizeSub] = ls;
+                }
+                if (take) {
+                    s_fl[kAfTake] = 1;
+                    s_sc[kScLogpSub] = logp;
+                    s_sc[kScEnergySub] = energy;
+                }
+                const int n_lvl = s_fl[kAfNLvl];
+                bool turning = false;
+                for (int l = 0; l < n_lvl; ++l) turning = turning || (ssum[1 + 2 * l] <= 0.0) || (ssum[2 + 2 * l] <= 0.0);
+                if (turning) {
+                    s_fl[kAfTurning] = 1;
+                    valid = false;
+                }
+            } else {
+                s_fl[kAfDiverging] = 1;
+                valid = false;
+            }
+
+            const int max_depth = (draw < a.tune && draw < a.early_draws) ? a.early_depth : a.max_depth;
+            bool end_transition = false;
+            if (!valid) {
+                end_transition = true;
+                s_fl[kAfTake] = 0;
+                depth += 1;                                       // PyMC3 counts the discarded doubling in `depth`
+            } else if (leaf == (1 << depth) - 1) {
+                const double z1 = s_sc[kScLogSizeTree], z2 = s_sc[kScLogSizeSub];
+                const double u = t2_chain_uniform(p, c, draw, kPurposeTop, (unsigned)depth);
+                if (log(u) < z2 - z1) {
+                    s_fl[kAfTakeTop] = 1;
+                    s_sc[kScLogpProp] = s_sc[kScLogpSub];
+                    s_sc[kScEnergyProp] = s_sc[kScEnergySub];
+                }
+                s_sc[kScLogSizeTree] = logaddexp_d(z1, z2);
+                s_fl[kAfMerge] = 1;
+                s_fl[kAfDirPrev] = dir;
+                depth += 1;
+                if (ssum[kAqTree0] <= 0.0 || ssum[kAqTree0 + 1] <= 0.0) {
+                    s_fl[kAfTurning] = 1;
+                    end_transition = true;
+                }
+                if (depth >= max_depth) end_transition = true;
+                if (!end_transition) {
+                    const double ud = t2_chain_uniform(p, c, draw, kPurposeDir, (unsigned)depth);
+                    const int dir_new = (ud < 0.5) ? 1 : -1;
+                    if (dir_new != dir) {     // the next doubling grows the other end of the tree: its edge is the other buffer
+                        s_fl[kAfFlip] = 1;
+                        s_fl[kAfW] ^= 1;
+                    }
+                    dir = dir_new;
+                    leaf = 0;
+                    s_fl[kAfFirst] = 1;
+                    s_sc[kScLogSizeSub] = -INFINITY;
+                }
+            } else {
+                leaf += 1;
+            }
+
+            if (end_transition) {
+                const bool tuning = draw < a.tune;
+                const double n = fmax(s_sc[kScNProp], 1.0);
+                const double accept = s_sc[kScAcceptSum] / n;
+                const double eps_used = s_sc[kScEps];
+                if (tuning) {     // step_size.DualAverageAdaptation.update
+                    const double count = s_sc[kScDaCount];
+                    const double w = 1.0 / (count + p.da_t0);
+                    const double hbar = (1.0 - w) * s_sc[kScDaHbar] + w * (p.target_accept - accept);
+                    const double log_step = s_sc[kScDaMu] - hbar * sqrt(count) / p.da_gamma;
+                    const double mk = pow(count, -p.da_kappa);
+                    s_sc[kScDaLogBar] = mk * log_step + (1.0 - mk) * s_sc[kScDaLogBar];
+                    s_sc[kScDaHbar] = hbar;
+                    s_sc[kScDaCount] = count + 1.0;
+                    s_sc[kScDaLogStep] = log_step;
+                    s_sc[kScEps] = exp(log_step);
+                }
+                if (a.stats) {
+                    double* st = a.stats + (size_t)draw * BGH_NUTS_N_STATS * p.C;
+                    st[0 * p.C + c] = (double)depth;
+                    st[1 * p.C + c] = accept;
+                    st[2 * p.C + c] = s_sc[kScNProp];
+                    st[3 * p.C + c] = (double)s_fl[kAfDiverging];
+                    st[4 * p.C + c] = s_sc[kScEnergyProp];
+                    st[5 * p.C + c] = tuning ? s_sc[kScEps] : eps_used;
+                    st[6 * p.C + c] = s_sc[kScLogpProp];
+                    st[7 * p.C + c] = s_sc[kScMaxDE];
+                }
+                s_fl[kAfRecSlot] = (draw >= a.tune) ? (int)(draw - a.tune) : -1;
+                if (tuning) {     // QuadPotentialDiagAdapt.update schedule
+                    const int n_adapt = s_fl[kAfNAdapt];
+                    double fg = s_sc[kScFgW] + 1.0, bg = s_sc[kScBgW] + 1.0;
+                    s_sc[kScFgUse] = fg;
+                    s_sc[kScBgUse] = bg;
+                    s_fl[kAfAdapt] = 1;
+                    const int sw = (n_adapt > 0 && n_adapt % a.window == 0) ? 1 : 0;
+                    s_fl[kAfSwitch] = sw;
+                    if (sw) { fg = bg; bg = 0.0; }
+                    s_sc[kScFgW] = fg;
+                    s_sc[kScBgW] = bg;
+                    s_fl[kAfNAdapt] = n_adapt + 1;
+                }
+                draw += 1;
+                if (draw == a.tune) s_sc[kScEps] = exp(s_sc[kScDaLogBar]);    // stop tuning
+                if (draw >= (long long)a.tune + a.draws) {
+                    phase = kPhaseFlush;
+                } else {
+                    s_fl[kAfNew] = 1;
+                    depth = 0;
+                    leaf = 0;
+                    const double ud = t2_chain_uniform(p, c, draw, kPurposeDir, 0u);
+                    dir = (ud < 0.5) ? 1 : -1;
+                    s_sc[kScLogSizeSub] = -INFINITY;
+                }
+            }
+            s_fl[kAfPhase] = phase;
+            s_fl[kAfDraw] = (int)draw;
+            s_fl[kAfDepth] = depth;
+            s_fl[kAfLeaf] = leaf;
+            s_fl[kAfDir] = dir;
+            s_sc[kScH] = 0.5 * s_sc[kScEps] * (double)dir;
+            t2_schedule_leaf(s_fl, leaf, depth);
+            s.misc[0] = pack_cmd(s_fl, phase);
+            if (cmd_rare(s.misc[0])) {      // the rare-event path reads these from global memory
+                t2_afl(a, kAfRecSlot, c) = s_fl[kAfRecSlot];
+                t2_afl(a, kAfDraw, c) = s_fl[kAfDraw];
+                sc(p, kScFgUse, c) = s_sc[kScFgUse];
+                sc(p, kScBgUse, c) = s_sc[kScBgUse];
+            }
+        }
+        __syncthreads();
+        if (tr) tr[7] = global_timer_ns();
+        // ---- F: rare-event work and first half step of the next leapfrog for the late rows
+        const int bits_new = s.misc[0];
+        const double h_new = s.sc[kScH];
+        if (cmd_rare(bits_new) || (bits_new & kCbFlip)) {
+            t2_late_enter(t, s, c, bits_new, h_new);          // generic path: reloads the rows from global memory
+        } else {
+            // the chain simply continues: the row's state is still in registers
+            if (has_row) row_half_step(p, bits_new, h_new, i, wo, qv, mom_new, gnew, var, pol);
+            if (tid == 0) { s.sc[kScKin0LateLocal] = 0.0; s.sc[kScKin0LateRep] = 0.0; }
+            __syncthreads();
+        }
+        t2_store_chain(t, s, c, bits_new);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Sharded evaluation (bgh_logp_grad_sharded on contexts with replicated genes): likelihood pass | grid barrier | per-chain
 // closing with the peer exchange, one launch per rank.  The chain CTAs reduce the CTA partials and the slot sums of the
 // split genes themselves, so the payload of a chain (4 sums + the replicated genes' residual sums) is complete inside
@@ -984,20 +1363,7 @@ __device__ __forceinline__ void eval2_close(const Eval2Params& e, unsigned char*
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (lane == 0) s.sum[warp] = acc;
         }
-        for (int k = warp; k < f.n_split; k += kLikWarps) {
-            const int s0 = f.split_ptr[k], n = f.split_ptr[k + 1] - s0;
-            double tot = 0.0;
-            if (k < f.n_long) {
-                double acc = 0.0;
-                if (lane < kLikWarps)
-                    for (int i = lane; i < n; i += kLikWarps) acc += f.slots[(size_t)f.split_slots[s0 + i] * Cp + c];
-                for (int w = 0; w < kLikWarps; ++w) tot += __shfl_sync(0xffffffffu, acc, w);
-            } else {
-                const double x = lane < n ? f.slots[(size_t)f.split_slots[s0 + lane] * Cp + c] : 0.0;
-                for (int i = 0; i < n; ++i) tot += __shfl_sync(0xffffffffu, x, i);
-            }
-            if (lane == 0) s.sr[k] = tot;
-        }
+        split_gene_sums(f, c, s.sr);
         __syncthreads();
         const bool single = e.peer.world <= 1;
         if (!single) {
@@ -1054,6 +1420,10 @@ __global__ void __launch_bounds__(kLikThreads, 1) nuts_tick2_kernel(const __grid
     double* const s_kin0c = reinterpret_cast<double*>(smem_raw + kT2Kin0Offset);     // [kT2MaxChains]
     int* const s_np = reinterpret_cast<int*>(s_kin0c + kT2MaxChains);                  // [kT2MaxChains]
     int* const s_rows = reinterpret_cast<int*>(smem_raw + kT2RowsOffset);
+    int* const s_lrow = reinterpret_cast<int*>(smem_raw + kT2LateOffset);
+    const int n_late = t2_n_late(t);
+    if (n_late <= kLikThreads)
+        for (int r = threadIdx.x; r < n_late; r += kLikThreads) s_lrow[r] = t2_late_row(t, r) | (t2_late_replicated(t, r) ? kLateRep : 0);
     // the rows this CTA owns (constant for the whole run): gene ids into shared memory
     T2Own own;
     {
@@ -1088,11 +1458,16 @@ __global__ void __launch_bounds__(kLikThreads, 1) nuts_tick2_kernel(const __grid
             if (u) atomicOr(&s_need, u);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {     // chains with rare-event work, in chain order
+        if (threadIdx.x < 32) {     // chains with rare-event work, in chain order (ballot + prefix count per 32 chains)
             int n = 0;
-            for (int c = 0; c < p.C; ++c)
-                if (cmd_rare(s_bits[c])) s_np[n++] = c;
-            s_nnp = n;
+            for (int c0 = 0; c0 < p.C; c0 += 32) {
+                const int c = c0 + threadIdx.x;
+                const bool rare = c < p.C && cmd_rare(s_bits[c]);
+                const unsigned m = __ballot_sync(0xffffffffu, rare);
+                if (rare) s_np[n + __popc(m & ((1u << threadIdx.x) - 1u))] = c;
+                n += __popc(m);
+            }
+            if (threadIdx.x == 0) s_nnp = n;
         }
         __syncthreads();
         if (tr) { tr[11] = global_timer_ns(); tr[14] = (unsigned long long)s_nnp; tr[15] = (unsigned long long)own.n; }
@@ -1108,7 +1483,8 @@ __global__ void __launch_bounds__(kLikThreads, 1) nuts_tick2_kernel(const __grid
         if (tr) tr[1] = global_timer_ns();
         grid_barrier(t.bar, target, t.status);
         if (tr) tr[2] = global_timer_ns();
-        tick2_scalar(t, smem_raw, (unsigned)(t.tick_base + tick), tr);
+        if (n_late <= kLikThreads) tick2_scalar(t, smem_raw, (unsigned)(t.tick_base + tick), tr, s_bits, s_h, s_lrow, n_late);
+        else tick2_scalar_generic(t, smem_raw, (unsigned)(t.tick_base + tick), tr);
         if (tr) tr[3] = global_timer_ns();
         grid_barrier(t.bar, target, t.status);
         if (tr) tr[4] = global_timer_ns();

@@ -6,6 +6,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 
 
 def _run(env_extra=None):
@@ -25,7 +26,9 @@ def test_reference_arm_line(built_lib):
     assert d["value"] > 0 and d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"]
+    # the same `config` object as the CUDA arm prints (the driver compares the two)
+    import bench
+    assert d["config"] == bench.bench_config(bench.WORKLOADS["cfg1"], bench.WORKLOADS["cfg1"]["C"])
 
 
 def test_reference_arm_other_ranks_are_silent(built_lib):
