@@ -64,14 +64,15 @@ class bgh_nuts_cfg(ctypes.Structure):
         ("da_t0", ctypes.c_double),
         ("n_dim_total", ctypes.c_int32),
         ("coord_offset", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 4),
+        ("chain_offset", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 3),
     ]
 
 
 class bgh_nuts_async_buffers(ctypes.Structure):
     _fields_ = [("base", bgh_nuts_buffers), ("afl", ctypes.c_void_p), ("trace", ctypes.c_void_p),
                 ("run_stats", ctypes.c_void_p), ("trace_f32", ctypes.c_int32), ("reserved", ctypes.c_int32),
-                ("k6", ctypes.c_void_p)]
+                ("k6", ctypes.c_void_p), ("head_trace", ctypes.c_void_p)]
 
 
 NUTS_ASYNC_N_FL, NUTS_ASYNC_N_SC, NUTS_ASYNC_PARTIALS = 26, 24, 24
@@ -80,6 +81,7 @@ NUTS_MAX_PARTIALS = 1 + 2 * NUTS_MAX_DEPTH
 NUTS_SLOT_Q, NUTS_SLOT_GRAD, NUTS_SLOT_VAR = 0, 1, 2
 NUTS_SLOT_FG_MEAN, NUTS_SLOT_FG_RAW, NUTS_SLOT_BG_MEAN, NUTS_SLOT_BG_RAW = 16, 17, 18, 19
 NUTS_SC_EPS, NUTS_SC_LOGP = 0, 1
+NUTS_AF_BAD_START = 21      # kAfBadStart (csrc/bgh_sampler.h): the energy at the start of a transition was not finite
 
 _vp = ctypes.c_void_p
 _i32, _i64, _dbl = ctypes.c_int32, ctypes.c_int64, ctypes.c_double

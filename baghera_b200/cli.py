@@ -31,6 +31,9 @@ def _common(p, with_snp_thr):
                         "(one host thread, engine and sampler kernel per device); default: --device only")
     p.add_argument("--seed", type=int, default=20211, help="Philox seed (the reference is unseeded)")
     p.add_argument("--trace-dtype", default="float64", choices=["float64", "float32"])
+    p.add_argument("--stream-stats", default="auto", choices=["auto", "on", "off"],
+                   help="accumulate the per-gene mean / variance / P while sampling and keep only an fp32 trace for the quantiles "
+                        "(auto: when the fp64 trace would exceed 8 GiB)")
 
 
 def build_parser():
@@ -65,7 +68,13 @@ def main(argv=None):
               "run it with the reference tool." % a.command, file=sys.stderr)
         return 2
     devices = [int(x) for x in a.devices.split(",")] if a.devices else None
-    gr.OPTIONS.update(device=devices[0] if devices else a.device, seed=a.seed, trace_dtype=a.trace_dtype, devices=devices)
+    n_dev = len(devices) if devices else 1
+    if (a.n_chains + n_dev - 1) // n_dev > 128:
+        # the persistent sampler kernel runs one CTA per chain and at most 128 chains per context (bgh_nuts_run)
+        print("--n-chains %d: at most 128 chains per device (use --devices to spread the chains over more GPUs)" % a.n_chains, file=sys.stderr)
+        return 2
+    gr.OPTIONS.update(device=devices[0] if devices else a.device, seed=a.seed, trace_dtype=a.trace_dtype, devices=devices,
+                      stream_stats={"auto": None, "on": True, "off": False}[a.stream_stats])
     chrom = a.chromosome if a.chromosome == "all" else a.chromosome
     if a.command == "gene-heritability":
         cmd.gene_heritability(a.input_snp_filename, a.output_genes_filename, a.output_summary_filename, a.logger_filename,

@@ -1291,7 +1291,7 @@ static int nuts_params(bgh_ctx* ctx, const bgh_nuts_buffers* buf, const bgh_nuts
     p->state = buf->state; p->ckpt = buf->ckpt; p->sc = buf->sc; p->fl = buf->fl; p->partials = buf->partials;
     p->sums = buf->sums; p->logp_w = buf->logp_w; p->n_active = buf->n_active_dev;
     p->D = ctx->D; p->Cp = ctx->Cp; p->C = ctx->cfg.n_chains; p->n_vec_blocks = 2 * ctx->sm_count;
-    p->coord_offset = cfg->coord_offset; p->seed = cfg->seed; p->draw = draw;
+    p->coord_offset = cfg->coord_offset; p->seed = cfg->seed; p->draw = draw; p->chain_offset = cfg->chain_offset;
     p->head_rows = 0; p->own_head = 1; p->own_first = 1; p->status = ctx->d_status; p->gcoord = ctx->d_gcoord;
     memset(&p->peer, 0, sizeof(p->peer));
     if (sharded) {
@@ -1474,6 +1474,7 @@ static int nuts_run_tick2(bgh_ctx* ctx, const bgh_nuts_async_buffers* buf, const
     { const char* e = getenv("BGH_T2_TRACE_CTA"); t.trace_cta = e ? atoi(e) : 0; }
     { const char* e = getenv("BGH_TRACE_TICK"); t.trace_first = e ? atoi(e) : 0; }
     t.k6 = buf->k6;
+    t.head_trace = buf->head_trace;
     fill_ll_peer(ctx, true, &t.peer);
     t.peer.epoch_base = ctx->t2_epoch;
     t.phase_trace = ctx->d_trace;   // NULL unless bgh_debug_trace enabled it (tools/time_tick2.py)
@@ -1534,7 +1535,7 @@ int bgh_nuts_run(bgh_ctx* ctx, const bgh_nuts_async_buffers* buf, const bgh_nuts
     AsyncParams a;
     int rc = nuts_params(ctx, &buf->base, cfg, 0, &a.n);
     if (rc != BGH_OK) return rc;
-    const bool needs_v2 = a.n.peer.world > 1 || buf->k6 != nullptr || !buf->trace;
+    const bool needs_v2 = a.n.peer.world > 1 || buf->k6 != nullptr || buf->head_trace != nullptr || !buf->trace;
     if (a.n.peer.world > 1 && (tick_v1(ctx, true) || (ctx->cfg.n_shared_rows != ctx->cfg.n_replicated)))
         return fail(ctx, BGH_ESTATE, "bgh_nuts_run: sharded contexts need replicated-gene sharding (n_replicated) and the fused "
                                      "sampler kernel; other sharded contexts use bgh_nuts_transition");

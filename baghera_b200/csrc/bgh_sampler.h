@@ -60,6 +60,7 @@ struct NutsParams {
     // head_rows = 0, coord_offset = 0, own_* = 1, peer.world <= 1.
     int coord_offset, head_rows, own_head, own_first;
     const int* gcoord;  // optional [D]: global coordinate of every local row (bgh_set_row_coords), or NULL
+    int chain_offset;   // index of this context's chain 0 among all chains of the analysis (Philox key)
     PeerParams peer;    // sums are all-reduced over peer memory inside the scalar kernels when peer.world > 1
     int* status;        // device status word (peer time-out), may be NULL on a single rank
     unsigned long long seed;

@@ -33,8 +33,8 @@ __device__ __forceinline__ double u01_open(unsigned a, unsigned b)
 }
 __device__ __forceinline__ uint2 chain_key(const NutsParams& p, int chain)
 {
-    return make_uint2((unsigned)(p.seed & 0xffffffffull) ^ (0x9E3779B9u * (unsigned)(chain + 1)),
-                      (unsigned)(p.seed >> 32) + (unsigned)chain);
+    const unsigned g = (unsigned)(chain + p.chain_offset);
+    return make_uint2((unsigned)(p.seed & 0xffffffffull) ^ (0x9E3779B9u * (g + 1u)), (unsigned)(p.seed >> 32) + g);
 }
 enum : unsigned { kPurposeMomentum = 1, kPurposeDir = 2, kPurposeLeaf = 3, kPurposeTop = 4 };
 

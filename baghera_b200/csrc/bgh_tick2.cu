@@ -159,6 +159,7 @@ __device__ __forceinline__ double row_rare(const Tick2Params* tp, int bits, int 
             if (a.trace_f32) reinterpret_cast<float*>(a.trace)[t] = (float)qp;
             else reinterpret_cast<double*>(a.trace)[t] = qp;
         }
+        if (tp->head_trace != nullptr && d < tp->row0) tp->head_trace[((size_t)rec_slot * p.C + ch) * tp->row0 + d] = qp;
         if (tp->k6 != nullptr && d >= tp->row0) {
             // streaming posterior statistics of the per-gene effects (ref: gene_regression.py:165-174, :283, :314)
             const bool gamma = tp->lik.model == BGH_MODEL_GENE_GAMMA;

@@ -74,6 +74,7 @@ struct Tick2Params {
     int trace_cta;           // tools: the CTA whose phase stamps are recorded
     int trace_first;         // tools: first traced tick
     double* k6;              // optional [3][D][Cp]: sum beta, sum beta^2, count(beta - mi > 0) of the recorded draws
+    double* head_trace;      // optional [draws][C][row0]: the shared parameters of every recorded draw, fp64
     T2Peer peer;
     unsigned long long* phase_trace;   // tools: [64 ticks][16] globaltimer stamps of CTA trace_cta, or NULL
 };

@@ -17,7 +17,17 @@ from . import stats as st
 # run-time options that have no slot in the reference signature (set by command / cli)
 # ``devices``: list of CUDA ordinals -> the chains run as independent replicas over these GPUs (replicas.py);
 # None = the single ``device``
-OPTIONS = dict(device=0, seed=20211, trace_dtype="float64", progress=None, devices=None)
+# ``stream_stats``: None = automatic (on when the fp64 trace would exceed STREAM_ABOVE_BYTES: the kernel then accumulates the
+# per-gene mean / variance / P(beta > mi) in fp64 while sampling (K6), keeps the shared parameters of every draw in fp64, and the
+# stored positions — only needed for the per-gene quantiles — shrink to fp32); True / False force it
+OPTIONS = dict(device=0, seed=20211, trace_dtype="float64", progress=None, devices=None, stream_stats=None)
+STREAM_ABOVE_BYTES = 8 << 30
+
+
+def _use_stream_stats(draws, chains, D):
+    if OPTIONS["stream_stats"] is not None:
+        return bool(OPTIONS["stream_stats"])
+    return 8 * int(draws) * int(chains) * int(D) > STREAM_ABOVE_BYTES
 
 
 def build_gene_index(snp_dataset):
@@ -44,23 +54,34 @@ def device_quantiles(x, qs):
     return out
 
 
-def gene_posterior_table(trace, genes, chunk=512):
+def gene_posterior_table(trace, genes, chunk=512, k6=None, head=3):
     """Per-gene posterior statistics (ref: gene_regression.py:165-177) from the device trace
-    [draws, D, C]: P = mean(beta - mi > 0), bg_mean/median/var/5perc/95perc over all draws and chains."""
+    [draws, D, C]: P = mean(beta - mi > 0), bg_mean/median/var/5perc/95perc over all draws and chains.
+
+    k6 [3, D, C] (streaming sums of the sampler kernel, fp64): P, mean and variance come from it — exact whatever the
+    trace's dtype — and the trace only serves the quantiles."""
     import torch
     draws, D, C = trace.shape
-    G = D - 3
-    mi = torch.sigmoid(trace[:, 2, :].double())                     # [draws, C]
+    G = D - head
+    mi = torch.sigmoid(trace[:, head - 1, :].double())              # [draws, C]
     cols = {k: np.empty(G) for k in ("P", "bg_mean", "bg_median", "bg_var", "bg_5perc", "bg_95perc")}
+    if k6 is not None:
+        n = float(draws * C)
+        tot = k6[:, head:, :].double().sum(dim=2)                   # [3, G]
+        mean = tot[0] / n
+        cols["bg_mean"][:] = mean.cpu().numpy()
+        cols["bg_var"][:] = (tot[1] / n - mean * mean).cpu().numpy()
+        cols["P"][:] = (tot[2] / n).cpu().numpy()
     for g0 in range(0, G, chunk):
         g1 = min(G, g0 + chunk)
-        b = trace[:, 3 + g0:3 + g1, :].double()                     # [draws, g, C]
-        P = ((b - mi[:, None, :]) > 0).double().mean(dim=(0, 2))
+        b = trace[:, head + g0:head + g1, :].double()               # [draws, g, C]
         flat = b.permute(0, 2, 1).reshape(draws * C, g1 - g0)
         q5, q50, q95 = device_quantiles(flat, (5.0, 50.0, 95.0))
-        cols["P"][g0:g1] = P.cpu().numpy()
-        cols["bg_mean"][g0:g1] = flat.mean(dim=0).cpu().numpy()
-        cols["bg_var"][g0:g1] = flat.var(dim=0, unbiased=False).cpu().numpy()
+        if k6 is None:
+            P = ((b - mi[:, None, :]) > 0).double().mean(dim=(0, 2))
+            cols["P"][g0:g1] = P.cpu().numpy()
+            cols["bg_mean"][g0:g1] = flat.mean(dim=0).cpu().numpy()
+            cols["bg_var"][g0:g1] = flat.var(dim=0, unbiased=False).cpu().numpy()
         cols["bg_median"][g0:g1] = q50.cpu().numpy()
         cols["bg_5perc"][g0:g1] = q5.cpu().numpy()
         cols["bg_95perc"][g0:g1] = q95.cpu().numpy()
@@ -98,19 +119,22 @@ def analyse_normal(snps_object, output_summary_filename, output_logger, SWEEPS, 
         return Engine(chi2, ld, cat32, G, c, int(n_chains), model="gene", fix_intercept=bool(fix_intercept), device=device)
 
     devices = OPTIONS["devices"] or [OPTIONS["device"]]
-    dt = torch.float32 if OPTIONS["trace_dtype"] == "float32" else torch.float64
+    stream = _use_stream_stats(SWEEPS, CHAINS, G + 3)
+    dt = torch.float32 if (OPTIONS["trace_dtype"] == "float32" or stream) else torch.float64
     start = synth.jittered_start(G + 3, int(CHAINS), seed=OPTIONS["seed"] + 1, model="gene")
     # nuts_kwargs=dict(target_accept=0.90)
+    torch.cuda.reset_peak_memory_stats()
     out, n_launches = sample_on_devices(make_engine, start, int(SWEEPS), int(TUNE), devices, OPTIONS["seed"],
-                                        trace_dtype=dt, progress=OPTIONS["progress"], target_accept=0.90)
+                                        trace_dtype=dt, progress=OPTIONS["progress"], target_accept=0.90, stream_stats=stream)
     trace = out["trace"]                                           # [draws, D, C], unconstrained space
     n_div = int(out["stats"][int(TUNE):, 3].sum())
     if n_div:
         logging.warning("There were %d divergences after tuning. Increase `target_accept` or reparameterize." % n_div)
 
-    tW = torch.exp(trace[:, 0, :].double()).cpu().numpy()           # W  = exp(W_log__)
-    te = trace[:, 1, :].double().cpu().numpy()
-    tmi = torch.sigmoid(trace[:, 2, :].double()).cpu().numpy()      # mi = sigmoid(mi_logodds__)
+    heads = out["head_trace"] if stream else trace[:, :3, :].double()   # shared parameters of every draw, fp64
+    tW = torch.exp(heads[:, 0, :]).cpu().numpy()                    # W  = exp(W_log__)
+    te = heads[:, 1, :].cpu().numpy()
+    tmi = torch.sigmoid(heads[:, 2, :]).cpu().numpy()               # mi = sigmoid(mi_logodds__)
     w = torch.as_tensor(Mg / float(N_1kG), dtype=torch.float64, device=trace.device)
     therTOT = torch.einsum("dgc,g->dc", trace[:, 3:, :].double(), w).cpu().numpy()   # (:83)
 
@@ -132,12 +156,14 @@ def analyse_normal(snps_object, output_summary_filename, output_logger, SWEEPS, 
     output_logger.info(" Heritability: " + str(mi_mean) + " (std= " + str(mi_std) + ")\n" + "[ 5th perc= "
                        + str(mi_5perc) + "," + " 95 perc= " + str(mi_95perc) + "]\n")
 
-    df = gene_posterior_table(trace, genes)
+    df = gene_posterior_table(trace, genes, k6=out["k6"] if stream else None)
     df["mi_mean"] = mi_mean
     df["mi_median"] = mi_median
     analyse_normal.last_run = dict(seconds_tune=out["seconds_tune"], seconds_draws=out["seconds_draws"],
+                                   seconds_total=out.get("seconds_total"), ticks=out.get("ticks"),
                                    leapfrogs=out["leapfrogs"], stats=out["stats"], kernel_launches=n_launches,
-                                   devices=out["devices"])
+                                   devices=out["devices"], stream_stats=stream, trace_dtype=str(dt),
+                                   peak_hbm_bytes=int(torch.cuda.max_memory_allocated()))
     logging.info("analysis done")
     return df
 

@@ -12,7 +12,8 @@ import threading
 import numpy as np
 
 
-def sample_on_devices(make_engine, start, draws, tune, devices, seed, trace_dtype=None, progress=None, target_accept=0.90):
+def sample_on_devices(make_engine, start, draws, tune, devices, seed, trace_dtype=None, progress=None, target_accept=0.90,
+                      stream_stats=False):
     """make_engine(device, n_chains) -> Engine; start: float64[C, D] start points of ALL chains.
     Returns (out, launches): out as NutsSampler.sample (trace [draws, D, C] on devices[0], stats [n, 8, C], ...)."""
     import torch
@@ -31,10 +32,12 @@ def sample_on_devices(make_engine, start, draws, tune, devices, seed, trace_dtyp
             torch.cuda.set_device(dev)
             eng = make_engine(dev, len(idx))
             try:
-                # chain_key mixes (seed, local chain index): every block needs its own seed
-                smp = NutsSampler(eng, seed=seed + 7919 * i, target_accept=target_accept)
-                smp.init(start[idx])
-                out = smp.sample(int(draws), int(tune), trace_dtype=trace_dtype, progress=progress if i == 0 else None)
+                # Philox keys by the GLOBAL chain index and the start mean over ALL chains: the draws do not depend on the
+                # device list (--devices 0,1 reproduces --device 0)
+                smp = NutsSampler(eng, seed=seed, target_accept=target_accept, chain_offset=int(idx[0]))
+                smp.init(start[idx], start_mean=start.mean(axis=0))
+                out = smp.sample(int(draws), int(tune), trace_dtype=trace_dtype, progress=progress if i == 0 else None,
+                                 stream_stats=stream_stats)
                 torch.cuda.synchronize(dev)
                 results[i] = (out, eng.launch_count)
             finally:
@@ -59,6 +62,9 @@ def sample_on_devices(make_engine, start, draws, tune, devices, seed, trace_dtyp
     if len(outs) > 1:
         merged["trace"] = torch.cat([o["trace"].to(dev0, non_blocking=True) for o in outs], dim=2)
         merged["stats"] = np.concatenate([o["stats"] for o in outs], axis=2)
+        if stream_stats:
+            merged["k6"] = torch.cat([o["k6"].to(dev0, non_blocking=True) for o in outs], dim=2)
+            merged["head_trace"] = torch.cat([o["head_trace"].to(dev0, non_blocking=True) for o in outs], dim=2)
         merged["leapfrogs"] = np.mean([o["leapfrogs"] for o in outs], axis=0)
         merged["ticks"] = int(max(o["ticks"] for o in outs))
         for k in ("seconds_tune", "seconds_draws", "seconds_total"):

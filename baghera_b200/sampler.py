@@ -28,7 +28,7 @@ EARLY_MAX_TREEDEPTH, MAX_TREEDEPTH, EARLY_DRAWS = 8, 10, 200
 
 
 class NutsSampler:
-    def __init__(self, engine, seed=20211, target_accept=0.90, row_coords=None, n_dim_total=0):
+    def __init__(self, engine, seed=20211, target_accept=0.90, row_coords=None, n_dim_total=0, chain_offset=0):
         """row_coords / n_dim_total: gene-block sharded engines only (``Shard.row_coords()`` and the global D): every
         rank runs its own NutsSampler over its rows of q; the per-chain sums are exchanged over NVLink peer memory
         inside the sampler's kernels and the momentum normals are keyed by the global coordinate, so all ranks take
@@ -65,6 +65,7 @@ class NutsSampler:
         cfg.target_accept = float(target_accept)
         cfg.coord_offset = 0
         cfg.n_dim_total = int(n_dim_total)
+        cfg.chain_offset = int(chain_offset)      # chains dealt to several devices: Philox keys by the global chain index
         if row_coords is not None:
             engine.set_row_coords(row_coords)
         self.cfg = cfg
@@ -94,13 +95,16 @@ class NutsSampler:
         return ctypes.c_void_p(self.t.cuda.current_stream(self.eng.device).cuda_stream)
 
     # ------------------------------------------------------------------ init='jitter+adapt_diag'
-    def init(self, q0_cd):
-        """q0_cd: float64[C, D] start points (test point + U(-1,1) jitter per chain)."""
+    def init(self, q0_cd, start_mean=None):
+        """q0_cd: float64[C, D] start points (test point + U(-1,1) jitter per chain).  start_mean: mean of the start points
+        of ALL chains of the analysis when this sampler runs a block of them (jitter+adapt_diag seeds the mass-matrix
+        estimator with it); default: the mean of q0_cd."""
         t = self.t
         q0 = np.asarray(q0_cd, dtype=np.float64)
         self.state[NUTS_SLOT_Q].copy_(self.eng.to_device_layout(q0))
         self.state[NUTS_SLOT_VAR].fill_(1.0)
-        mean = t.as_tensor(q0.mean(axis=0), dtype=t.float64, device=self.eng.device)
+        mean = t.as_tensor(q0.mean(axis=0) if start_mean is None else np.asarray(start_mean, dtype=np.float64),
+                           dtype=t.float64, device=self.eng.device)
         self.state[NUTS_SLOT_FG_MEAN].copy_(mean[:, None].expand(-1, self.eng.Cp))
         self.state[NUTS_SLOT_FG_RAW].fill_(INITIAL_WEIGHT)          # raw_var = initial_diag * weight
         self.state[NUTS_SLOT_BG_MEAN].zero_()
@@ -142,10 +146,15 @@ class NutsSampler:
               self.eng.ctx)
 
     # ------------------------------------------------------------------ pm.sample, asynchronous chains
-    def sample(self, draws, tune, trace_dtype=None, progress=None, poll_ticks=64):
+    def sample(self, draws, tune, trace_dtype=None, progress=None, poll_ticks=64, stream_stats=False, keep_trace=True):
         """pm.sample(draws, tune=tune): the whole run on the device (bgh_nuts_run).  Every tick advances
         every chain by one leapfrog; chains never wait for the deepest tree of the batch.  Returns the
-        same dict as :meth:`sample_lockstep` (``leapfrogs`` holds the per-draw mean tree size over chains)."""
+        same dict as :meth:`sample_lockstep` (``leapfrogs`` holds the per-draw mean tree size over chains).
+
+        stream_stats: the kernel also accumulates, per coordinate and chain, {sum, sum of squares, count(value - mi > 0)} of
+        the recorded per-gene effects in fp64 (``k6`` [3, D, C]) and keeps the shared parameters of every draw in fp64
+        (``head_trace`` [draws, H, C]) — the per-gene table of ref: gene_regression.py:165-174 then needs the stored positions
+        only for its quantiles (an fp32 trace is enough) or not at all (keep_trace=False)."""
         t = self.t
         eng = self.eng
         C = eng.C
@@ -154,13 +163,18 @@ class NutsSampler:
             raise ValueError("trace dtype must be float64 or float32")
         # the device writes the trace chain-major [draws, C, D] (contiguous per chain); callers see the
         # reference-shaped view [draws, D, C]
-        trace_cd = t.empty((max(draws, 1), C, eng.D), dtype=dt, device=eng.device)
-        trace = trace_cd.permute(0, 2, 1)
+        trace_cd = t.empty((max(draws, 1), C, eng.D), dtype=dt, device=eng.device) if keep_trace else None
+        trace = trace_cd.permute(0, 2, 1) if keep_trace else None
+        H = 3 if eng.model == "gene" else 2
+        k6 = t.zeros((3, eng.D, eng.Cp), dtype=t.float64, device=eng.device) if stream_stats else None
+        head = t.zeros((max(draws, 1), C, H), dtype=t.float64, device=eng.device) if stream_stats else None
         stats = t.zeros((tune + draws, NUTS_N_STATS, C), dtype=t.float64, device=eng.device)
         ab = bgh_nuts_async_buffers()
         ab.base = self.buf
         ab.afl = self.afl.data_ptr()
-        ab.trace = trace_cd.data_ptr()
+        ab.trace = trace_cd.data_ptr() if keep_trace else None
+        ab.k6 = k6.data_ptr() if stream_stats else None
+        ab.head_trace = head.data_ptr() if stream_stats else None
         ab.run_stats = stats.data_ptr()
         ab.trace_f32 = int(dt == t.float32)
         n_ticks = ctypes.c_int64(0)
@@ -170,15 +184,20 @@ class NutsSampler:
                                   int(poll_ticks), self._stream(), ctypes.byref(n_ticks)), eng.ctx)
         t.cuda.synchronize(eng.device)
         total = time.perf_counter() - t0
-        if int(self.afl[21, :C].sum().item()) != 0:          # kAfBadStart
+        if int(self.afl[_lib.NUTS_AF_BAD_START, :C].sum().item()) != 0:
             raise ValueError("Bad initial energy: the energy at the start of a transition was not finite")
         st = stats.cpu().numpy()
         tree = st[:, 2, :]                                   # leapfrogs per transition and chain
         frac_tune = tree[:tune].sum() / max(tree.sum(), 1.0)
         self.total_leapfrogs += int(n_ticks.value)
         self.draw += tune + draws
-        return dict(trace=trace[:draws], stats=st, leapfrogs=tree.mean(axis=1), ticks=int(n_ticks.value),
-                    seconds_tune=total * frac_tune, seconds_draws=total * (1.0 - frac_tune), seconds_total=total, tune=tune)
+        out = dict(trace=trace[:draws] if keep_trace else None, stats=st, leapfrogs=tree.mean(axis=1), ticks=int(n_ticks.value),
+                   seconds_tune=total * frac_tune, seconds_draws=total * (1.0 - frac_tune), seconds_total=total, tune=tune,
+                   seconds_note="seconds_total is measured; tune / draws are apportioned by the leapfrogs of each phase")
+        if stream_stats:
+            out["k6"] = k6[:, :, :C]
+            out["head_trace"] = head[:draws].permute(0, 2, 1)          # [draws, H, C]
+        return out
 
     # ------------------------------------------------------------------ pm.sample, lock-step chains
     def sample_lockstep(self, draws, tune, trace_dtype=None, progress=None):

@@ -241,7 +241,10 @@ typedef struct bgh_nuts_cfg {
     int32_t n_dim_total;    /* D over all ranks (step-size rule); 0 => bgh_dim(ctx) */
     int32_t coord_offset;   /* sharded contexts: genes in front of this rank's gene block (local per-gene row d is
                              * global row d + coord_offset; the shared rows keep their index); 0 on a single rank */
-    int32_t reserved[4];
+    int32_t chain_offset;   /* index of this context's chain 0 among all chains of the analysis (chains dealt to several
+                             * devices): the Philox key of a chain is derived from (seed, chain_offset + chain), so the
+                             * draws do not depend on how the chains are spread over devices */
+    int32_t reserved[3];
 } bgh_nuts_cfg;
 
 void bgh_nuts_cfg_default(bgh_nuts_cfg* cfg);
@@ -297,6 +300,8 @@ typedef struct bgh_nuts_async_buffers {
                      * {sum v, sum v^2, count(v - mi > 0)}, v = beta_g (normal model) or N_1kG * beta_g (gamma model) for
                      * the per-gene rows: the per-gene posterior table of gene_regression.py:165-174 without the trace.
                      * With k6 set, `trace` may be NULL (no positions stored). */
+    double* head_trace; /* optional [draws][C][H] fp64, H = rows in front of the per-gene rows (3 normal, 2 gamma / genome-wide):
+                         * the shared parameters of every recorded draw in full precision when `trace` is fp32 or absent */
 } bgh_nuts_async_buffers;
 
 int bgh_nuts_run(bgh_ctx* ctx, const bgh_nuts_async_buffers* buf, const bgh_nuts_cfg* cfg, int32_t tune,

@@ -101,3 +101,54 @@ def test_gene_heritability_gamma_end_to_end(snp_csv):
     log = open(out_l).read()
     for needle in ("gene level regression, model: gamma", " Intercept: ", " heritability from genes: ", " Heritability: "):
         assert needle in log, needle
+
+
+def test_streaming_statistics_equal_the_full_trace_table(snp_csv):
+    """K6: the per-gene mean / variance / P accumulated inside the sampler kernel (fp64 sums per coordinate and chain) equal
+    the table computed from the full fp64 trace of the same run; the shared parameters kept in fp64 equal the trace's; the
+    quantiles from an fp32 copy of the trace agree to fp32 rounding.  BASELINE config-1 shape."""
+    import torch
+    from baghera_b200 import gene_regression as gr
+    from baghera_b200.engine import Engine
+    from baghera_b200.sampler import NutsSampler
+    d = synth.make_arrays(20_000, 200)
+    eng = Engine(d.chi2, d.ld, d.gene_id, d.G, d.c, 4)
+    s = NutsSampler(eng, seed=4)
+    s.init(synth.jittered_start(d.G + 3, 4, seed=5))
+    out = s.sample(400, 150, stream_stats=True)
+    tr = out["trace"]                                                     # fp64 [draws, D, C]
+    assert torch.equal(out["head_trace"], tr[:, :3, :])
+    genes = ["g%d" % i for i in range(d.G)]
+    full = gr.gene_posterior_table(tr, genes)
+    stream = gr.gene_posterior_table(tr.float(), genes, k6=out["k6"])
+    for col in ("bg_mean", "P"):
+        assert np.allclose(stream[col], full[col], rtol=1e-12, atol=1e-15), col
+    assert np.allclose(stream["bg_var"], full["bg_var"], rtol=1e-9, atol=1e-16)      # E[x^2] - E[x]^2 vs two-pass
+    for col in ("bg_median", "bg_5perc", "bg_95perc"):
+        assert np.allclose(stream[col], full[col], rtol=1e-6, atol=1e-7), col
+    # without any stored positions the sums are still there
+    s2 = NutsSampler(eng, seed=4)
+    s2.init(synth.jittered_start(d.G + 3, 4, seed=5))
+    out2 = s2.sample(400, 150, stream_stats=True, keep_trace=False)
+    assert out2["trace"] is None and torch.equal(out2["k6"], out["k6"]) and torch.equal(out2["head_trace"], out["head_trace"])
+    eng.close()
+
+
+def test_devices_do_not_change_the_draws():
+    """Philox keys by the global chain index: a block of chains sampled by its own context (as --devices does) draws what
+    the same chains draw inside the full batch."""
+    from baghera_b200.engine import Engine
+    from baghera_b200.sampler import NutsSampler
+    d = synth.make_arrays(5000, 20, seed=4)
+    q0 = synth.jittered_start(d.G + 3, 4, seed=1)
+    eng = Engine(d.chi2, d.ld, d.gene_id, d.G, d.c, 4)
+    s = NutsSampler(eng, seed=9)
+    s.init(q0)
+    a = s.sample(20, 30)["trace"].cpu().numpy()
+    eng.close()
+    eng2 = Engine(d.chi2, d.ld, d.gene_id, d.G, d.c, 2)
+    s2 = NutsSampler(eng2, seed=9, chain_offset=2)
+    s2.init(q0[2:], start_mean=q0.mean(axis=0))
+    b = s2.sample(20, 30)["trace"].cpu().numpy()
+    eng2.close()
+    assert np.allclose(a[:, :, 2:], b, rtol=1e-9, atol=1e-12)
