@@ -136,7 +136,11 @@ def analyse_normal(snps_object, output_summary_filename, output_logger, SWEEPS, 
     te = heads[:, 1, :].cpu().numpy()
     tmi = torch.sigmoid(heads[:, 2, :]).cpu().numpy()               # mi = sigmoid(mi_logodds__)
     w = torch.as_tensor(Mg / float(N_1kG), dtype=torch.float64, device=trace.device)
-    therTOT = torch.einsum("dgc,g->dc", trace[:, 3:, :].double(), w).cpu().numpy()   # (:83)
+    acc = torch.zeros((trace.shape[0], trace.shape[2]), dtype=torch.float64, device=trace.device)
+    for g0 in range(0, G, 512):                                     # herTOT = sum(beta * Mg / N_1kG), gene chunks (:83)
+        g1 = min(G, g0 + 512)
+        acc += torch.einsum("dgc,g->dc", trace[:, 3 + g0:3 + g1, :].double(), w[g0:g1])
+    therTOT = acc.cpu().numpy()
 
     if CHAINS > 1:
         logging.info("evaluating Gelman-Rubin")

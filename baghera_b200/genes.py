@@ -9,20 +9,6 @@ import pandas as pd
 COLUMNS = ["gene", "chrom", "n_snps", "ld_min", "ld_max", "ld_var", "stats_min", "stats_max", "stats_avg"]
 
 
-def get_stats(group):
-    """ref: genes.py:13-26 (one gene's SNP rows -> descriptive statistics)."""
-    return pd.Series({
-        "chrom": int(group["chr"].values[0]),
-        "n_snps": len(group),
-        "ld_min": group["l"].min(),
-        "ld_max": group["l"].max(),
-        "ld_var": np.var(group["l"].values),
-        "stats_min": group["stats"].min(),
-        "stats_max": group["stats"].max(),
-        "stats_avg": group["stats"].mean(),
-    })
-
-
 class Genes(object):
     def __init__(self):
         self.filename = None

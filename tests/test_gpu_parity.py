@@ -224,3 +224,60 @@ def test_gamma_model(cfg1, C, fix):
     for i in range(C):
         assert grad_rel_err(g[i], g_ref[i]) <= REL_TOL, "chain %d" % i
     eng.close()
+
+
+def test_cfg2_four_chains_at_full_size():
+    """cfg2: 1.1M SNPs x 15k genes with the reference's default 4 chains — the <4,1> chain-lane geometry (8 SNP ranges per
+    warp) at full size, every chain against the oracle."""
+    d = synth.make_arrays(1_100_000, 15_000)
+    eng = _engine(d, 4)
+    _check(eng, d, synth.jittered_start(d.G + 3, 4, seed=21))
+    eng.close()
+
+
+def test_cfg5_genome_wide_model_at_ten_million_snps():
+    """cfg5: genome-wide model (ref: heritability.py:44-55) on a 10M-SNP synthetic set, 64 chains; oracle on 3 chains plus the
+    exact identity sum r^2/l = S3 - 2 e S2 + e^2 S1 - 2 b (B - e n) + b^2 A (sufficient statistics) on all of them."""
+    import torch
+    from baghera_b200.engine import Engine
+    d = synth.make_arrays(10_000_000, 1, seed=11)
+    C = 64
+    eng = Engine(d.chi2, d.ld, None, 1, d.c, C, model="gw")
+    rng = np.random.default_rng(5)
+    Q = np.stack([rng.normal(1.0, 0.3, C), rng.normal(-1.0, 1.0, C)], axis=1)
+    logp, grad = eng.logp_grad(eng.to_device_layout(Q))
+    torch.cuda.synchronize()
+    lp = logp[:C].cpu().numpy()
+    g = eng.from_device_layout(grad).cpu().numpy()
+    chi2, ld = d.chi2.astype(np.float64), d.ld.astype(np.float64)
+    for i in (0, 31, 63):
+        lp_ref, g_ref = mo.gw_logp_grad_closed(Q[i], chi2, ld, d.c)
+        assert abs(lp[i] - lp_ref) <= REL_TOL * abs(lp_ref)
+        assert grad_rel_err(g[i], g_ref) <= REL_TOL
+    # all chains: d logp / d e = -(e - 1) + S2 - e S1 - c mi A1, with S1 = sum 1/l, S2 = sum s/l, A1 = number of SNPs
+    S1, S2, n = np.sum(1.0 / ld), np.sum(chi2 / ld), float(len(ld))
+    mi = 1.0 / (1.0 + np.exp(-Q[:, 1]))
+    ge = -(Q[:, 0] - 1.0) + S2 - Q[:, 0] * S1 - d.c * mi * n
+    assert np.max(np.abs(g[:, 0] - ge) / np.abs(ge)) <= REL_TOL
+    eng.close()
+
+
+def test_gamma_model_at_full_size():
+    """-m gamma at 1.1M SNPs x 15k genes, 64 chains: oracle on 2 chains."""
+    import torch
+    from baghera_b200.engine import Engine
+    d = synth.make_arrays(1_100_000, 15_000)
+    C = 64
+    eng = Engine(d.chi2, d.ld, d.gene_id, d.G, float(d.n_patients), C, model="gamma", gamma_rate=float(d.N_1kG))
+    Q = synth.jittered_start(d.G + 2, C, seed=77, model="gamma")
+    Q[:, 0] = 1.0 + 1e-3 * np.random.default_rng(1).normal(size=C)
+    logp, grad = eng.logp_grad(eng.to_device_layout(Q))
+    torch.cuda.synchronize()
+    lp = logp[:C].cpu().numpy()
+    g = eng.from_device_layout(grad).cpu().numpy()
+    lp_ref, g_ref = mo.gamma_batch_closed(Q[[0, 63]], d.chi2.astype(np.float64), d.ld.astype(np.float64), d.gene_id.astype(np.int64),
+                                          float(d.n_patients), float(d.N_1kG), False)
+    for k, i in enumerate((0, 63)):
+        assert abs(lp[i] - lp_ref[k]) <= REL_TOL * abs(lp_ref[k])
+        assert grad_rel_err(g[i], g_ref[k]) <= REL_TOL
+    eng.close()
