@@ -471,7 +471,7 @@ int bgh_create(bgh_ctx** out, const bgh_cfg* cfg)
     }
     ctx->sm_count = cfg->sm_count_override > 0 ? cfg->sm_count_override : prop.multiProcessorCount;
     ctx->n_cta = ctx->sm_count;
-    ctx->n_groups = ctx->n_cta * kLikWarps * (32 / ctx->CL);
+    ctx->n_groups = ctx->n_cta * kLikWarps;     // one SNP range per warp, whatever the chain geometry
     e = lik_configure();
     if (e == cudaSuccess) e = fused_configure();
     if (e == cudaSuccess) e = tick2_configure();
@@ -651,7 +651,7 @@ int bgh_upload(bgh_ctx* ctx, const float* chi2, const float* ld, const int32_t* 
     const bool fp = gw ? true : ctx->cfg.first_gene_partial != 0;
     const bool lp = gw ? true : ctx->cfg.last_gene_partial != 0;
     std::string err;
-    int rc = build_plan(Mp, g_sorted.data(), G, ctx->n_cta, kLikWarps * (32 / ctx->CL), fp, lp, ctx->cfg.first_gene_row,
+    int rc = build_plan(Mp, g_sorted.data(), G, ctx->n_cta, kLikWarps, fp, lp, ctx->cfg.first_gene_row,
                         ctx->cfg.last_gene_row, plan_kappa(), &ctx->plan, &err, kLikBatch, ctx->cfg.n_replicated,
                         ctx->cfg.owns_replicated != 0);
     if (rc != BGH_OK) return fail(ctx, rc, err);
@@ -659,7 +659,7 @@ int bgh_upload(bgh_ctx* ctx, const float* chi2, const float* ld, const int32_t* 
     {
         const char* ek = getenv("BGH_NUTS_KAPPA");
         const char* es = getenv("BGH_NUTS_SNAP");
-        rc = build_plan(Mp, g_sorted.data(), G, ctx->n_cta, kLikWarps * (32 / ctx->CL), fp, lp, ctx->cfg.first_gene_row,
+        rc = build_plan(Mp, g_sorted.data(), G, ctx->n_cta, kLikWarps, fp, lp, ctx->cfg.first_gene_row,
                         ctx->cfg.last_gene_row, (ek && *ek) ? atof(ek) : 60.0, &ctx->plan2, &err, kLikBatch, ctx->cfg.n_replicated,
                         ctx->cfg.owns_replicated != 0, (es && *es) ? atof(es) : 0.5);
         if (rc != BGH_OK) return fail(ctx, rc, err);
@@ -667,7 +667,7 @@ int bgh_upload(bgh_ctx* ctx, const float* chi2, const float* ld, const int32_t* 
     // rows each CTA owns in the fused sampler kernel (bgh_tick2.cu): genes complete inside one SNP range of the CTA
     {
         const Plan& P = ctx->plan2;
-        const int gpc = kLikWarps * (32 / ctx->CL);
+        const int gpc = kLikWarps;
         ctx->own_ptr.assign((size_t)ctx->n_cta + 1, 0);
         ctx->own_gene.clear();
         for (int cta = 0; cta < ctx->n_cta; ++cta) {

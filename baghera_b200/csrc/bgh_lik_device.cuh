@@ -14,15 +14,19 @@
 //     and the three sums every evaluation needs are plain FMA accumulations (3 DFMA):
 //         sum r^2 / l = sum rho^2        sum r / l = sum rho wp        sum_{j in g} r = sum rho lp
 //     => 5 FP64 instructions per (SNP, chain); nothing is converted inside the kernel.
-//   * A *group* of CL lanes owns one contiguous SNP range and walks it sequentially; each lane of the
-//     group carries CPL chains.  Because every lane of a group sees the same SNP, a gene boundary is
-//     group-uniform: the per-gene residual sum is a sequential fp64 accumulation that is flushed
-//     with one coalesced store when the gene id changes — the "segmented reduction" needs no
-//     shuffles and no atomics and is bit-reproducible.
-//   * Staging: one elected lane per group moves each chunk of the four arrays global -> shared with
-//     bulk asynchronous copies (cp.async.bulk, the 1-D TMA path) that complete on a group-private
-//     mbarrier; two stages per group, so the copy of chunk k+2 is issued as soon as chunk k is
-//     consumed.  All lanes then broadcast-read the chunk (LDS.128, 2 SNPs per load).
+//   * A WARP owns one contiguous SNP range and walks it sequentially in batches of 8 SNPs (genes are padded to
+//     whole batches, so a gene boundary only occurs between batches and is warp-uniform).  Lanes are laid out as
+//     SL = 32 / CL "SNP lanes" x CL chain lanes, each lane carrying CPL chains: with 64 chains (CL = 32, CPL = 2)
+//     every lane sees every SNP; with few chains (C = 4: CL = 4, SL = 8) the 8 SNPs of a batch are spread over the
+//     8 SNP lanes of each chain — all 32 lanes work, and the range count does not grow with 32 / CL (a range per
+//     CL lanes, the round-1 mapping, cut the 1.1M SNPs into 19k ranges at C = 4: nearly every gene was split over
+//     several ranges and its sum re-assembled from slots).  The per-gene residual sum is a sequential fp64
+//     accumulation per lane, folded over the SNP lanes by a fixed xor-shuffle tree when the gene ends and flushed
+//     with one coalesced store: no atomics, bit-reproducible.
+//   * Staging: one elected lane per warp moves each 128-SNP chunk of the four arrays global -> shared with
+//     bulk asynchronous copies (cp.async.bulk, the 1-D TMA path) that complete on a warp-private
+//     mbarrier; two stages, so the copy of chunk k+2 is issued as soon as chunk k is consumed.  All lanes then
+//     read the chunk from shared memory (CL = 32: broadcast LDS.128, 2 SNPs per load).
 //   * ranges that start or end inside a gene (NonCoding spans ~45% of all SNPs) write "slot"
 //     partials; the finalize step sums the slots of each such gene in a fixed order.
 #pragma once
@@ -105,8 +109,8 @@ constexpr double kGwFixHi = 1.0000001;
 // doubles of padding shift consecutive groups by 16 bytes so that the per-group broadcast LDS.128 of
 // the SL groups fall into different banks (and keep every bulk-copy destination 16-byte aligned).
 constexpr int kStages = 2;
-constexpr int kStride = kChunk + 2 * 8;    // fp64 arrays: up to 8 groups per warp, +2 doubles each
-constexpr int kStrideG = kChunk + 4 * 8;   // gene ids: +4 ints per group keeps 16-byte alignment
+constexpr int kStride = kChunk + 2 * 8;    // fp64 arrays (the slack keeps the three arrays of a stage in different banks)
+constexpr int kStrideG = kChunk + 4 * 8;   // gene ids
 constexpr size_t kWarpStageBytes = (size_t)kStride * 3 * sizeof(double) + (size_t)kStrideG * sizeof(int);
 static_assert(kWarpStageBytes % 16 == 0, "warp staging area must keep 16-byte alignment");
 constexpr size_t kLikStageBytes = (size_t)kLikWarps * kStages * kWarpStageBytes;
@@ -152,20 +156,19 @@ template <int CL, int CPL, bool GAMMA>
 __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* smem_raw, const int cta, const int chain_block,
                                           uint32_t& par)
 {
-    constexpr int SL = 32 / CL;     // groups per warp
-    constexpr int CH = 4 * CL;      // SNPs per group per chunk (SL * CH == kChunk)
+    constexpr int SL = 32 / CL;     // SNP lanes per chain lane
+    constexpr int CH = kChunk;      // SNPs per chunk
     constexpr int CG = CL * CPL;    // chains per chain block
     constexpr int B = kLikBatch;    // SNPs per branch-free batch
-    static_assert(SL * CH == kChunk, "chunk geometry");
     static_assert(CH % B == 0, "batch must divide the chunk");
-    static_assert(SL <= 8, "at most 8 groups per warp");
+    static_assert(SL <= B && B % SL == 0, "the SNP lanes share a batch evenly");
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int grp = lane / CL;
+    const int grp = lane / CL;      // SNP lane: takes SNPs grp, grp + SL, ... of every batch
     const int lc = lane % CL;
-    const unsigned gmask = (CL == 32) ? 0xffffffffu : (((1u << CL) - 1u) << (grp * CL));
-    const int v = (cta * kLikWarps + warp) * SL + grp;
+    constexpr unsigned gmask = 0xffffffffu;
+    const int v = cta * kLikWarps + warp;
     const int Cp = p.Cp;
     const int ch0 = chain_block * CG + lc;   // chain of slot k is ch0 + k*CL
     constexpr bool gamma_model = GAMMA;     // compile-time: keeps exp() and the extra selects out of the normal model's code
@@ -173,7 +176,7 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
     const int row0 = gamma_model ? 2 : 3;   // first per-gene row of q / grad
 
     unsigned char* const warp_stage = smem_raw + (size_t)warp * kStages * kWarpStageBytes;
-    const uint32_t bar0 = smem_u32(smem_raw + kLikStageBytes) + 8u * (uint32_t)((warp * kStages) * 8 + grp);   // stage s: + 64 s
+    const uint32_t bar0 = smem_u32(smem_raw + kLikStageBytes) + 8u * (uint32_t)((warp * kStages) * 8);   // stage s: + 64 s
     BGH_TRACE(0);
     if (p.trace != nullptr && lane == 0)
         p.trace[((size_t)(chain_block * p.n_cta + cta) * kLikWarps + warp) * 8 + 7] = sm_id();
@@ -208,15 +211,15 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
         const size_t b0 = (size_t)base0 + (size_t)k * CH;
         const uint32_t bar = bar0 + 64u * st;
         unsigned char* const sb = warp_stage + (size_t)st * kWarpStageBytes;
-        const uint32_t d_s = smem_u32(reinterpret_cast<double*>(sb) + grp * (CH + 2));
-        const uint32_t d_g = smem_u32(reinterpret_cast<int*>(reinterpret_cast<double*>(sb) + 3 * kStride) + grp * (CH + 4));
+        const uint32_t d_s = smem_u32(reinterpret_cast<double*>(sb));
+        const uint32_t d_g = smem_u32(reinterpret_cast<int*>(reinterpret_cast<double*>(sb) + 3 * kStride));
         mbar_expect_tx(bar, CH * 28);
         bulk_g2s(d_s, p.sp + b0, CH * 8, bar, pol);
         bulk_g2s(d_s + kStride * 8, p.wp + b0, CH * 8, bar, pol);
         bulk_g2s(d_s + 2 * kStride * 8, p.lp + b0, CH * 8, bar, pol);
         bulk_g2s(d_g, p.gid + b0, CH * 4, bar, pol);
     };
-    if (lc == 0) {
+    if (lane == 0) {
         if (n_chunks > 0) issue(0);
         if (n_chunks > 1) issue(1);
     }
@@ -253,7 +256,7 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
         }
     }
 
-    if (cta == 0 && warp == 0 && grp == 0) {   // hand the per-chain constants to finalize
+    if (cta == 0 && warp == 0 && grp == 0) {   // hand the per-chain constants to finalize (one SNP lane suffices)
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
             p.cc[0 * Cp + ch0 + k * CL] = iW2[k];
@@ -291,6 +294,12 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
         // gene `cur` is complete within this range (or the range ends): emit its sum
         auto flush = [&](bool final_flush) {
             bool owner;
+            if (SL > 1 && !exclusive) {     // fold the SNP lanes' partial sums of the gene (fixed xor tree)
+#pragma unroll
+                for (int o = CL; o < 32; o <<= 1)
+#pragma unroll
+                    for (int k = 0; k < CPL; ++k) ag[k] += __shfl_xor_sync(0xffffffffu, ag[k], o);
+            }
             if (exclusive) {
                 // every group of this CTA accumulates the same gene: reduced in the CTA epilogue
 #pragma unroll
@@ -299,7 +308,9 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
             } else {
                 const bool to_head = (cur == g_first) && head_partial;
                 const bool to_tail = !to_head && final_flush && tail_partial;
-                if (to_head || to_tail) {
+                if (grp != 0) {
+                    // the other SNP lanes hold copies of the folded sum: SNP lane 0 stores
+                } else if (to_head || to_tail) {
                     double* dst = p.slots + (size_t)(to_head ? v : p.NG + v) * Cp + ch0;
 #pragma unroll
                     for (int k = 0; k < CPL; ++k) dst[k * CL] = ag[k];
@@ -315,7 +326,7 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
                 }
                 owner = !to_head;   // this group holds the gene's first SNP: it owns the prior terms
             }
-            if (owner) {
+            if (owner && grp == 0) {    // (the epilogue adds the SNP lanes: the prior terms are counted by SNP lane 0)
 #pragma unroll
                 for (int k = 0; k < CPL; ++k) {
                     s1[k] += db[k];
@@ -348,10 +359,10 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
             const int base = base0 + kc * CH;
             unsigned char* const sb = warp_stage + (size_t)st * kWarpStageBytes;
             // SNP i (0 <= i < CH) of this group lives at index i of the group's slice of each array
-            const double* const sm_s = reinterpret_cast<const double*>(sb) + grp * (CH + 2);
+            const double* const sm_s = reinterpret_cast<const double*>(sb);
             const double* const sm_w = sm_s + kStride;
             const double* const sm_l = sm_w + kStride;
-            const int* const sm_g = reinterpret_cast<const int*>(reinterpret_cast<const double*>(sb) + 3 * kStride) + grp * (CH + 4);
+            const int* const sm_g = reinterpret_cast<const int*>(reinterpret_cast<const double*>(sb) + 3 * kStride);
             mbar_wait(bar0 + 64u * st, (par >> st) & 1u);
             par ^= 1u << st;
 
@@ -374,21 +385,34 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
                     }
                     enter_gene(g_i, tmp);
                 }
-                double2 s2v[B / 2], w2v[B / 2], l2v[B / 2];
+                if constexpr (SL == 1) {
+                    double2 s2v[B / 2], w2v[B / 2], l2v[B / 2];
 #pragma unroll
-                for (int t = 0; t < B / 2; ++t) {
-                    s2v[t] = *reinterpret_cast<const double2*>(sm_s + i + 2 * t);
-                    w2v[t] = *reinterpret_cast<const double2*>(sm_w + i + 2 * t);
-                    l2v[t] = *reinterpret_cast<const double2*>(sm_l + i + 2 * t);
-                }
+                    for (int t = 0; t < B / 2; ++t) {
+                        s2v[t] = *reinterpret_cast<const double2*>(sm_s + i + 2 * t);
+                        w2v[t] = *reinterpret_cast<const double2*>(sm_w + i + 2 * t);
+                        l2v[t] = *reinterpret_cast<const double2*>(sm_l + i + 2 * t);
+                    }
 #pragma unroll
-                for (int t = 0; t < B / 2; ++t) {
-                    accumulate(s2v[t].x, w2v[t].x, l2v[t].x);
-                    accumulate(s2v[t].y, w2v[t].y, l2v[t].y);
+                    for (int t = 0; t < B / 2; ++t) {
+                        accumulate(s2v[t].x, w2v[t].x, l2v[t].x);
+                        accumulate(s2v[t].y, w2v[t].y, l2v[t].y);
+                    }
+                } else {
+                    // SNP lane grp takes SNPs grp, grp + SL, ... of the batch (consecutive doubles across the SNP lanes)
+                    double sv[B / SL], wv[B / SL], lv[B / SL];
+#pragma unroll
+                    for (int t = 0; t < B / SL; ++t) {
+                        sv[t] = sm_s[i + grp + t * SL];
+                        wv[t] = sm_w[i + grp + t * SL];
+                        lv[t] = sm_l[i + grp + t * SL];
+                    }
+#pragma unroll
+                    for (int t = 0; t < B / SL; ++t) accumulate(sv[t], wv[t], lv[t]);
                 }
             }
             __syncwarp(gmask);
-            if (lc == 0 && kc + kStages < n_chunks) issue(kc + kStages);
+            if (lane == 0 && kc + kStages < n_chunks) issue(kc + kStages);
         }
         flush(true);
     }
@@ -423,7 +447,7 @@ __device__ __forceinline__ void lik_phase(const LikParams& p, unsigned char* sme
         }
     }
     __syncthreads();
-    const bool cta_exclusive = (p.groups[cta * kLikWarps * SL].z & kExclusive) != 0;
+    const bool cta_exclusive = (p.groups[cta * kLikWarps].z & kExclusive) != 0;
     for (int o = threadIdx.x; o < 5 * CG; o += blockDim.x) {
         const int which = o / CG, cc = o % CG;
         if (which == 4 && !cta_exclusive) continue;

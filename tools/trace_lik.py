@@ -25,7 +25,7 @@ lp = torch.empty(eng.Cp, dtype=torch.float64, device="cuda")
 g = torch.empty_like(q)
 check(eng.L.bgh_debug_trace(eng.ctx, 1, None, 0), eng.ctx)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-n_cta = int(eng.L.bgh_n_groups(eng.ctx)) // (16 * (1 if args.C > 16 else 32 // max(4, 1 << (args.C - 1).bit_length())))
+n_cta = int(eng.L.bgh_n_groups(eng.ctx)) // 16
 for it in range(4):
     if args.flush:
         flush.fill_(it)
