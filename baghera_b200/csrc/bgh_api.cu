@@ -1478,6 +1478,8 @@ static int nuts_run_tick2(bgh_ctx* ctx, const bgh_nuts_async_buffers* buf, const
     fill_ll_peer(ctx, true, &t.peer);
     t.peer.epoch_base = ctx->t2_epoch;
     t.phase_trace = ctx->d_trace;   // NULL unless bgh_debug_trace enabled it (tools/time_tick2.py)
+    if (ctx->d_trace)               // the evaluation kernels share the buffer (per-warp stamps): start from zeros
+        BGH_CUDA(ctx, cudaMemsetAsync(ctx->d_trace, 0, sizeof(unsigned long long) * (size_t)ctx->chain_blocks * ctx->n_cta * kLikWarps * 8, s));
 
     const int64_t max_ticks = (int64_t)(a.tune + a.draws) * 1024 + 1024;
     int64_t ticks = 0;

@@ -35,6 +35,15 @@ class Snps(object):
         1.1M rows); multi-character separators and ``native=False`` use ``pd.read_csv`` like the reference."""
         sep = "\t" if separator == "t" else separator
         if native and len(sep) == 1:
+            # the native reader covers the documented schema without quoting; anything else goes through pandas, like the
+            # reference (quoted fields with doubled quotes, extra columns whose dtype pandas would infer differently)
+            with open(input_snp_filename, "rb") as f:
+                head = f.read(1 << 16)
+            cols = head.split(b"\n", 1)[0].decode("utf-8", "replace").strip().split(sep)
+            schema = {"chr", "rs_id", "position", "cm", "maf", "l", "gene", "sample_size", "z"}
+            if b'"' in head or not set(c.strip() for c in cols) <= schema:
+                native = False
+        if native and len(sep) == 1:
             from . import ingest
             open(input_snp_filename).close()        # a missing file raises here, as in the reference
             try:

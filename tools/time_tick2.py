@@ -69,6 +69,9 @@ for ver, cta in runs:
             dur = (t[2:n, order[k + 1]] - t[2:n, order[k]]) / 1e3
             print("  %-36s p50 %6.2f  mean %6.2f  max %6.2f us" % (name, np.median(dur), dur.mean(), dur.max()))
         print("  tick total p50 %.2f us" % np.median(np.diff(t[2:n, 0]) / 1e3))
+        if os.environ.get("BGH_T2_RAW"):
+            for k in range(2, 6):
+                print("   raw tick", k, [int(x - t[k, 0]) if x > 1e15 else int(x) for x in t[k]])
         if os.environ.get("BGH_T2_DETAIL"):
             print("  own rows", t[2, 15], " per tick: n_rare cmd_us items_us(thread0) sync_us rest_us")
             for k in range(2, min(n, 40)):
