@@ -39,6 +39,7 @@ struct ChainSums {
 //   gw model  : {sg0 (sigmoid of x0 when the intercept is "fixed"), -, mi, lp0}
 struct ChainConst {
     double iW, iW2, mi, lp0;
+    double x0, x1;      // rows 0 and 1 of q as read for the constants (the closing formulas need e / x0 again)
 };
 
 __device__ __forceinline__ ChainConst chain_const(const FinParams& p, int ch)
@@ -50,6 +51,7 @@ __device__ __forceinline__ ChainConst chain_const(const FinParams& p, int ch)
         // beta_g ~ Gamma(alpha = mi, beta = rate) sampled as beta_log__:
         //   sum_g [ -lgamma(mi) + mi log(rate) - rate beta_g + (mi - 1) x_g + x_g ]   (x_g = log beta_g, Jacobian x_g)
         const double e = p.q[0 * p.ds + ch * p.cs], xm = p.q[1 * p.ds + ch * p.cs];
+        c.x0 = e; c.x1 = xm;
         const double ax = fabs(xm);
         const double u = exp(-ax);
         const double L = log1p(u);
@@ -67,6 +69,7 @@ __device__ __forceinline__ ChainConst chain_const(const FinParams& p, int ch)
     }
     if (p.model == BGH_MODEL_GENE_NORMAL) {
         const double xW = p.q[0 * p.ds + ch * p.cs], e = p.q[1 * p.ds + ch * p.cs], xm = p.q[2 * p.ds + ch * p.cs];
+        c.x0 = xW; c.x1 = e;
         const double ax = fabs(xm);
         const double u = exp(-ax);                 // one exp + one log1p serve sigmoid and both logs
         const double L = log1p(u);
@@ -83,6 +86,7 @@ __device__ __forceinline__ ChainConst chain_const(const FinParams& p, int ch)
         c.lp0 = lp;
     } else {
         const double x0 = p.q[0 * p.ds + ch * p.cs], xm = p.q[1 * p.ds + ch * p.cs];
+        c.x0 = x0; c.x1 = xm;
         const double ax = fabs(xm);
         const double u = exp(-ax);
         const double L = log1p(u);
@@ -112,21 +116,21 @@ __device__ __forceinline__ void chain_closing(const FinParams& p, int ch, const 
     g[0] = g[1] = g[2] = 0.0;
     if (p.model == BGH_MODEL_GENE_GAMMA) {
         // S1 = sum_g x_g, S2 = sum_g beta_g (owned genes)
-        const double e = p.q[0 * p.ds + ch * p.cs];
+        const double e = c.x0;
         logp = c.lp0 + c.mi * s.S1 - p.gamma_rate * s.S2 - 0.5 * s.A_ll;
         g[0] = -kGammaETau * (e - 1.0) + (p.fix ? 0.0 : s.A_e);
         g[1] = 1.0 - 2.0 * c.mi + c.mi * (1.0 - c.mi) * (c.iW + s.S1);
         return;
     }
     if (p.model == BGH_MODEL_GENE_NORMAL) {
-        const double e = p.q[1 * p.ds + ch * p.cs];
+        const double e = c.x1;
         const double G = (double)p.G_total;
         logp = c.lp0 - 0.5 * s.S2 * c.iW2 - 0.5 * s.A_ll;
         g[0] = c.iW - 1.0 + s.S2 * c.iW2 - G;
         g[1] = -(e - 1.0) + (p.fix ? 0.0 : s.A_e);
         g[2] = 1.0 - 2.0 * c.mi + c.mi * (1.0 - c.mi) * s.S1 * c.iW2;
     } else {
-        const double x0 = p.q[0 * p.ds + ch * p.cs];
+        const double x0 = c.x0;
         logp = c.lp0 - 0.5 * s.A_ll;
         if (p.fix) {
             const double sg = c.iW;

@@ -58,7 +58,9 @@ constexpr size_t kT2Kin0Offset = kT2CmdOffset + kT2CmdBytes;                  //
 constexpr int kT2MaxRowsSmem = 8192;
 constexpr size_t kT2RowsOffset = kT2Kin0Offset + kT2MaxChains * (sizeof(double) + sizeof(int));   // int[kT2MaxRowsSmem]
 constexpr size_t kT2LateOffset = kT2RowsOffset + kT2MaxRowsSmem * sizeof(int);   // int[kLikThreads] late-row table
-constexpr size_t kT2SmemBytes = kT2LateOffset + kLikThreads * sizeof(int);
+constexpr int kT2MaxSlotsSmem = 1024;
+constexpr size_t kT2SplitOffset = kT2LateOffset + kLikThreads * sizeof(int);     // int[kLikThreads + 1] list starts + int[kT2MaxSlotsSmem] slot ids
+constexpr size_t kT2SmemBytes = kT2SplitOffset + (kLikThreads + 1 + kT2MaxSlotsSmem) * sizeof(int);
 static_assert(kT2SmemBytes <= 227 * 1024, "shared memory of the fused sampler kernel");
 
 size_t tick2_smem_bytes() { return kT2SmemBytes; }
@@ -562,6 +564,27 @@ __device__ __forceinline__ void split_gene_sums(const FinParams& f, int c, doubl
     }
 }
 
+// the same sums with the (constant) slot lists cached in shared memory: one global round trip instead of three
+__device__ __forceinline__ void split_gene_sums_cached(const FinParams& f, int c, double* s_sr, const int* s_sptr, const int* s_sidx)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Cp = f.Cp;
+    for (int k = f.n_long + tid; k < f.n_split; k += blockDim.x) {
+        const int s0 = s_sptr[k], n = s_sptr[k + 1] - s0;
+        double tot = 0.0;
+        for (int i = 0; i < n; ++i) tot += f.slots[(size_t)s_sidx[s0 + i] * Cp + c];
+        s_sr[k] = tot;
+    }
+    for (int k = warp; k < f.n_long; k += kLikWarps) {
+        const int s0 = s_sptr[k], n = s_sptr[k + 1] - s0;
+        double acc = 0.0, tot = 0.0;
+        if (lane < kLikWarps)
+            for (int i = lane; i < n; i += kLikWarps) acc += f.slots[(size_t)s_sidx[s0 + i] * Cp + c];
+        for (int w = 0; w < kLikWarps; ++w) tot += __shfl_sync(0xffffffffu, acc, w);
+        if (lane == 0) s_sr[k] = tot;
+    }
+}
+
 // late rows of chain c: local index r in [0, n_late): head rows first, then the split genes in list order
 __device__ __forceinline__ int t2_n_late(const Tick2Params& t)
 {
@@ -987,7 +1010,8 @@ __device__ __noinline__ void tick2_scalar_generic(const Tick2Params& t, unsigned
 constexpr int kLateRep = 1 << 30;
 
 __device__ __forceinline__ void tick2_scalar(const Tick2Params& t, unsigned char* smem_raw, unsigned tick_global, unsigned long long* tr,
-                                             const int* s_bits, const double* s_h, const int* s_lrow, int n_late)
+                                             const int* s_bits, const double* s_h, const int* s_lrow, int n_late, const int* s_sptr,
+                                             const int* s_sidx, bool split_cached)
 {
     const AsyncParams& a = t.a;
     const NutsParams& p = a.n;
@@ -1033,46 +1057,62 @@ __device__ __forceinline__ void tick2_scalar(const Tick2Params& t, unsigned char
         gc.iW2 = gc.mi = gc.beta = 0.0;
         const int k_split = (!gw && d >= t.row0) ? tid - t.row0 : (gw && tid == 1 ? 0 : -1);     // split-gene index of this thread's row
         if (has_row && k_split >= 0) gc = load_gene_coef(fc, f.split_gene[k_split], c, true);
-        // likelihood sums in fin_phase's order (bit-identical logp / head gradients); sampler sums lane-strided + xor tree
-        for (int k = warp; k < kT2Nq; k += kLikWarps) {
-            const bool lik = k < kT2Lik;
-            if (!lik && !((used >> (k - kT2Lik)) & 1u)) {
-                if (lane == 0) s.sum[k] = 0.0;
-                continue;
-            }
-            const double* const src = lik ? t.lik.part + (size_t)k * p.Cp + c : t.part + (size_t)(k - kT2Lik) * p.Cp + c;
-            const size_t stride = (size_t)(lik ? kT2Lik : kAsyncPartials) * p.Cp;
-            double acc = 0.0;
+        // likelihood sums in fin_phase's order (bit-identical logp / head gradients); sampler sums lane-strided + xor tree.
+        // Warp w reduces quantities w and w + 16: the loads of both are issued before either is summed (one round trip).
+        {
+            const int k0 = warp, k1 = warp + kLikWarps;
+            const bool on0 = k0 < kT2Lik || ((used >> (k0 - kT2Lik)) & 1u);
+            const bool on1 = k1 < kT2Nq && ((used >> (k1 - kT2Lik)) & 1u);
+            const double* const src0 = k0 < kT2Lik ? t.lik.part + (size_t)k0 * p.Cp + c : t.part + (size_t)(k0 - kT2Lik) * p.Cp + c;
+            const size_t st0 = (size_t)(k0 < kT2Lik ? kT2Lik : kAsyncPartials) * p.Cp;
+            const double* const src1 = t.part + (size_t)(k1 - kT2Lik) * p.Cp + c;
+            const size_t st1 = (size_t)kAsyncPartials * p.Cp;
+            double a0 = 0.0, a1 = 0.0;
             for (int i0 = 0; i0 * 32 < f.n_cta; i0 += 8) {
-                double v[8];
+                double v[8], w[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int row = lane + 32 * (i0 + j);
-                    v[j] = row < f.n_cta ? src[(size_t)row * stride] : 0.0;
+                    v[j] = (on0 && row < f.n_cta) ? src0[(size_t)row * st0] : 0.0;
+                    w[j] = (on1 && row < f.n_cta) ? src1[(size_t)row * st1] : 0.0;
                 }
-                acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+                a0 += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+                a1 += ((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]));
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) s.sum[k] = acc;
+            for (int o = 16; o > 0; o >>= 1) {
+                a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            }
+            if (lane == 0) {
+                s.sum[k0] = a0;
+                if (k1 < kT2Nq) s.sum[k1] = a1;
+            }
         }
-        split_gene_sums(f, c, s.sr);
+        if (split_cached) split_gene_sums_cached(f, c, s.sr, s_sptr, s_sidx);
+        else         split_gene_sums(f, c, s.sr);
         __syncthreads();
         if (tr) tr[5] = global_timer_ns();
         if (tid == 0) s.sum[kT2Lik + kAqKin0] += s.sc[kScKin0LateLocal];   // fresh momenta of the late rows (refreshed last tick)
 
         double kin = 0.0, gnew = 0.0, mom_new = pw;
-        double acc[kAsyncPartials];
+        // per-thread accumulators of the row's contributions: shared memory, thread-interleaved [quantity][thread] behind the
+        // (at most 512) split-gene sums — a local-memory array costs a cache round trip per quantity on this latency path
+        double* const acc = s.sr + kLikThreads + tid;
+        constexpr int kAs = kLikThreads;
+        static_assert((32 * 16 + kT2MaxPay + 32 + 16 + kLikWarps + kLikWarps * kAsyncPartials + kMaxPeers * kT2MaxPay + 2 + kLikThreads +
+                       kAsyncPartials * kLikThreads) * sizeof(double) <= kLikStageBytes, "scalar phase accumulators");
+        const unsigned u_acc = used & ~(1u << kAqKin0);
 #pragma unroll 1
-        for (int j = 0; j < kAsyncPartials; ++j) acc[j] = 0.0;
+        for (int j = 1; j < kAsyncPartials; ++j)
+            if ((u_acc >> j) & 1u) acc[j * kAs] = 0.0;
         // fixed-order CTA sum of the used quantities of acc[] into s.sum (xor tree inside the warp, then the warps in order)
         auto reduce_acc = [&]() {
-            acc[0] = kin;
-            const unsigned u = used & ~(1u << kAqKin0);
+            const unsigned u = u_acc;
 #pragma unroll 1
             for (int j = 0; j < kAsyncPartials; ++j) {
                 if (!((u >> j) & 1u)) continue;
-                double x = acc[j];
+                double x = j == 0 ? kin : acc[j * kAs];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
                 if (lane == 0) s.red2[warp * kAsyncPartials + j] = x;
@@ -1087,7 +1127,8 @@ __device__ __forceinline__ void tick2_scalar(const Tick2Params& t, unsigned char
             __syncthreads();
             kin = 0.0;
 #pragma unroll 1
-            for (int j = 0; j < kAsyncPartials; ++j) acc[j] = 0.0;
+            for (int j = 1; j < kAsyncPartials; ++j)
+                if ((u >> j) & 1u) acc[j * kAs] = 0.0;
         };
         if (!single) {
             // ---- B: rank-local late rows (their residual sums are complete on this rank), then the exchange
@@ -1425,6 +1466,15 @@ __global__ void __launch_bounds__(kLikThreads, 1) nuts_tick2_kernel(const __grid
     const int n_late = t2_n_late(t);
     if (n_late <= kLikThreads)
         for (int r = threadIdx.x; r < n_late; r += kLikThreads) s_lrow[r] = t2_late_row(t, r) | (t2_late_replicated(t, r) ? kLateRep : 0);
+    // slot lists of the split genes (constant for the run)
+    int* const s_sptr = reinterpret_cast<int*>(smem_raw + kT2SplitOffset);
+    int* const s_sidx = s_sptr + kLikThreads + 1;
+    const int n_split = t.fin.n_split;
+    const bool split_cached = n_split <= kLikThreads && t.fin.split_ptr[n_split] <= kT2MaxSlotsSmem;
+    if (split_cached) {
+        for (int k = threadIdx.x; k <= n_split; k += kLikThreads) s_sptr[k] = t.fin.split_ptr[k];
+        for (int i = threadIdx.x; i < t.fin.split_ptr[n_split]; i += kLikThreads) s_sidx[i] = t.fin.split_slots[i];
+    }
     // the rows this CTA owns (constant for the whole run): gene ids into shared memory
     T2Own own;
     {
@@ -1484,7 +1534,7 @@ __global__ void __launch_bounds__(kLikThreads, 1) nuts_tick2_kernel(const __grid
         if (tr) tr[1] = global_timer_ns();
         grid_barrier(t.bar, target, t.status);
         if (tr) tr[2] = global_timer_ns();
-        if (n_late <= kLikThreads) tick2_scalar(t, smem_raw, (unsigned)(t.tick_base + tick), tr, s_bits, s_h, s_lrow, n_late);
+        if (n_late <= kLikThreads) tick2_scalar(t, smem_raw, (unsigned)(t.tick_base + tick), tr, s_bits, s_h, s_lrow, n_late, s_sptr, s_sidx, split_cached);
         else tick2_scalar_generic(t, smem_raw, (unsigned)(t.tick_base + tick), tr);
         if (tr) tr[3] = global_timer_ns();
         grid_barrier(t.bar, target, t.status);
