@@ -1135,7 +1135,7 @@ __device__ __forceinline__ void tick2_scalar(const Tick2Params& t, unsigned char
             if (has_row && !rep_row) {
                 gnew = gene_grad(fc, s.sr[k_split], gc);
                 stk(p.state + (size_t)kSlotGL * vec + wo + i, gnew, pol);
-                if (run) mom_new = row_finish(p, bits_old, h_old, i, wo, gnew, pw, var, tot, ck0, kin, acc, 1, pol);
+                if (run) mom_new = row_finish(p, bits_old, h_old, i, wo, gnew, pw, var, tot, ck0, kin, acc, kAs, pol);
             }
             if (run) reduce_acc();
             // payload = the chain's sums followed by the residual sums of the replicated genes (payload row 4 + j)
@@ -1182,7 +1182,7 @@ __device__ __forceinline__ void tick2_scalar(const Tick2Params& t, unsigned char
         if (has_row && rep_row) {
             gnew = k_split >= 0 ? gene_grad(fc, s.sr[k_split], gc) : s_hg[d];
             stk(p.state + (size_t)kSlotGL * vec + wo + i, gnew, pol);
-            mom_new = row_finish(p, bits_old, h_old, i, wo, gnew, pw, var, tot, ck0, kin, acc, 1, pol);
+            mom_new = row_finish(p, bits_old, h_old, i, wo, gnew, pw, var, tot, ck0, kin, acc, kAs, pol);
         }
         const double logp_now = s_hg[3];
         reduce_acc();
