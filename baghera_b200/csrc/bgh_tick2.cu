@@ -339,6 +339,8 @@ __device__ __forceinline__ void tick2_pre(const Tick2Params& t, const T2Own& own
 // POST: second half of the leapfrog with the gradient the likelihood pass just wrote, per-chain sums of the
 // CTA's rows -> part[cta][quantity][chain].  Accumulators live in the (idle) likelihood staging area,
 // thread-interleaved [quantity][thread], which is also the layout the CTA reduction reads.
+// LEVEL_MAJOR (few chains per CTA row: the pass is latency-bound) walks the checked tree levels outermost.
+template <bool LEVEL_MAJOR>
 __device__ __forceinline__ void tick2_post(const Tick2Params& t, const T2Own& own, const int* s_bits, const double* s_h, const double* s_kin0c,
                                            unsigned need, unsigned char* smem_raw)
 {
@@ -375,10 +377,66 @@ __device__ __forceinline__ void tick2_post(const Tick2Params& t, const T2Own& ow
                 ck0[u] = nl > 0 ? *t2_ckpt(p, lm, i[u]) : make_double2(0.0, 0.0);
                 for (int l = 1; l < nl; ++l) prefetch_l1(t2_ckpt(p, lm + l, i[u]));     // deeper levels: in flight with the row's other data
             }
+            if constexpr (!LEVEL_MAJOR) {
+#pragma unroll
+                for (int u = 0; u < kUPost; ++u) {
+                    if (r + u >= r1) break;
+                    row_finish(p, bits, h, i[u], wo, gn[u], ph[u], var[u], tot[u], ck0[u], kin, acc, kLikThreads, pol);
+                }
+                continue;
+            }
+            // row_finish for the kUPost rows, levels outermost: the checkpoint loads of one level are in flight for all
+            // rows at once (a warp holds 32 chains at different tree positions, so it walks max(nl) levels; one row at
+            // a time that is max(nl) dependent round trips PER ROW).  Every accumulator still receives the rows in
+            // ascending order: sums are bit-identical to row_finish.
+            double ps[kUPost], vel[kUPost];
+            const int sl = (bits >> kCbStoreShift) & 15;
 #pragma unroll
             for (int u = 0; u < kUPost; ++u) {
                 if (r + u >= r1) break;
-                row_finish(p, bits, h, i[u], wo, gn[u], ph[u], var[u], tot[u], ck0[u], kin, acc, kLikThreads, pol);
+                const double mom = fma(h, gn[u], ph[u]);
+                stk(p.state + (size_t)kSlotPL * vec + wo + i[u], mom, pol);
+                vel[u] = var[u] * mom;
+                kin = fma(0.5 * vel[u], mom, kin);
+                ps[u] = tot[u] + mom;
+                stk(p.state + (size_t)kSlotT * vec + i[u], ps[u], pol);
+                if (sl) *t2_ckpt(p, sl - 1, i[u]) = make_double2(mom, ps[u]);
+                if (nl > 0) {
+                    const double sub = ps[u] - ck0[u].y + ck0[u].x;
+                    acc[1 * kLikThreads] = fma(sub, var[u] * ck0[u].x, acc[1 * kLikThreads]);
+                    acc[2 * kLikThreads] = fma(sub, vel[u], acc[2 * kLikThreads]);
+                }
+            }
+#pragma unroll 1
+            for (int l = 1; l < nl; ++l) {
+                double a1 = acc[(1 + 2 * l) * kLikThreads], a2 = acc[(2 + 2 * l) * kLikThreads];
+#pragma unroll
+                for (int u0 = 0; u0 < kUPost; u0 += 2) {
+                    const double2 cka = *t2_ckpt(p, lm + l, i[u0]), ckb = *t2_ckpt(p, lm + l, i[u0 + 1]);   // a row past the end repeats row r
+                    if (r + u0 < r1) {
+                        const double sub = ps[u0] - cka.y + cka.x;
+                        a1 = fma(sub, var[u0] * cka.x, a1);
+                        a2 = fma(sub, vel[u0], a2);
+                    }
+                    if (r + u0 + 1 < r1) {
+                        const double sub = ps[u0 + 1] - ckb.y + ckb.x;
+                        a1 = fma(sub, var[u0 + 1] * ckb.x, a1);
+                        a2 = fma(sub, vel[u0 + 1], a2);
+                    }
+                }
+                acc[(1 + 2 * l) * kLikThreads] = a1; acc[(2 + 2 * l) * kLikThreads] = a2;
+            }
+            if (bits & kCbLast) {   // whole tree: its momentum sum is the running total; po = momentum at the opposite edge
+                const size_t wo_other = wo ? 0 : (size_t)kXStride * vec;
+                double a1 = acc[kAqTree0 * kLikThreads], a2 = acc[(kAqTree0 + 1) * kLikThreads];
+#pragma unroll
+                for (int u = 0; u < kUPost; ++u) {
+                    if (r + u >= r1) break;
+                    const double po = p.state[(size_t)kSlotPL * vec + wo_other + i[u]];
+                    a1 = fma(ps[u], vel[u], a1);
+                    a2 = fma(ps[u], var[u] * po, a2);
+                }
+                acc[kAqTree0 * kLikThreads] = a1; acc[(kAqTree0 + 1) * kLikThreads] = a2;
             }
         }
     }
@@ -1530,7 +1588,7 @@ __global__ void __launch_bounds__(kLikThreads, 1) nuts_tick2_kernel(const __grid
         fence_proxy_async();   // the staging area was written through the generic proxy (scalar phase, accumulators)
         for (int cb = 0; cb < t.chain_blocks; ++cb) lik_phase<CL, CPL, GAMMA>(t.lik, smem_raw, blockIdx.x, cb, par);
         if (tr) tr[9] = global_timer_ns();
-        tick2_post(t, own, s_bits, s_h, s_kin0c, s_need, smem_raw);
+        tick2_post<(CL * CPL < 64)>(t, own, s_bits, s_h, s_kin0c, s_need, smem_raw);
         if (tr) tr[1] = global_timer_ns();
         grid_barrier(t.bar, target, t.status);
         if (tr) tr[2] = global_timer_ns();
