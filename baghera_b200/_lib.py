@@ -119,6 +119,8 @@ SIGNATURES = {
     "bgh_n_groups": (_i32, [_vp]),
     "bgh_get_partition": (_i32, [_vp, _pi32, _i32]),
     "bgh_n_split_genes": (_i32, [_vp]),
+    "bgh_stream_len": (_i64, [_vp]),
+    "bgh_debug_stream": (_i32, [_vp, _i32, _vp, _i64]),
     "bgh_launch_count": (_i64, [_vp]),
     "bgh_set_profiling": (_i32, [_vp, _i32]),
     "bgh_kernel_time_ms": (_i32, [_vp, _pdbl, _pdbl, _pi64, _i32]),

@@ -299,6 +299,7 @@ struct bgh_ctx {
     bool uploaded = false;
     double lik_const = 0.0;
     Plan plan;
+    int64_t stream_len = 0;   // padded length of the device stream
     // device data
     double* d_xs = nullptr;   // prepared fp64 SoA {s/sqrt(l), 1/sqrt(l), sqrt(l)} (see bgh_lik_device.cuh)
     double* d_xw = nullptr;
@@ -398,6 +399,46 @@ static void pick_chain_geometry(int C, int* CL, int* CPL, int* Cp)
     else if (C <= 16) { *CL = 16; *CPL = 1; *Cp = 16; }
     else if (C <= 32) { *CL = 32; *CPL = 1; *Cp = 32; }
     else { *CL = 32; *CPL = 2; *Cp = ((C + 63) / 64) * 64; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bgh_upload on the device: the gene-sorted, padded, prepared fp64 stream is built from the raw fp32 columns.
+// The host keeps the one integer pass the work plan needs anyway (gene histogram; dest[j] = padded start of the
+// gene + number of earlier SNPs of the gene in file order, i.e. a STABLE counting sort); the scatter, the three
+// fp64 arrays (IEEE sqrt / divide: the same bits the host formulas give), the input validation and sum log(l) run
+// here.  ref: snps.py:117-134 hands (z^2, l, cat) to the model build, gene_regression.py:61-98.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPrepThreads = 256;
+__global__ void __launch_bounds__(kPrepThreads) prepare_stream_kernel(const float* __restrict__ chi2, const float* __restrict__ ld,
+                                                                      const int* __restrict__ dest, long long M, double* __restrict__ sp,
+                                                                      double* __restrict__ wp, double* __restrict__ lp,
+                                                                      double* __restrict__ log_part, int* __restrict__ bad)
+{
+    __shared__ double s_red[kPrepThreads / 32];
+    // block b owns the contiguous slice [b * per, (b + 1) * per): its sum of log(l) is a fixed-order sum (thread-strided
+    // within the slice, xor tree, warps in order), so the total is reproducible for a given M
+    const long long per = (M + gridDim.x - 1) / gridDim.x;
+    const long long j0 = (long long)blockIdx.x * per, j1 = min(M, j0 + per);
+    double acc = 0.0;
+    for (long long j = j0 + threadIdx.x; j < j1; j += kPrepThreads) {
+        const float lf = ld[j], sf = chi2[j];
+        if (!(lf > 0.0f) || !isfinite(lf) || !isfinite(sf)) { *bad = 1; continue; }
+        const double l = (double)lf, sq = sqrt(l);
+        const int d = dest[j];
+        sp[d] = (double)sf / sq;
+        wp[d] = 1.0 / sq;
+        lp[d] = sq;
+        acc += log(l);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kPrepThreads / 32; ++w) t += s_red[w];
+        log_part[blockIdx.x] = t;
+    }
 }
 
 extern "C" {
@@ -576,6 +617,18 @@ int bgh_debug_plan(int64_t M, const int32_t* gid_sorted, int32_t G, int32_t n_ct
 
 // Tools only: enable (buf != NULL -> allocate) per-warp phase timestamps of the likelihood kernel and
 // copy the last launch's trace [chain_blocks * n_cta * 16 warps][8] u64 to `out` (may be NULL).
+int64_t bgh_stream_len(const bgh_ctx* ctx) { return (ctx && ctx->uploaded) ? ctx->stream_len : 0; }
+
+int bgh_debug_stream(bgh_ctx* ctx, int32_t which, void* out, int64_t n)
+{
+    if (!ctx || !ctx->uploaded || !out || which < 0 || which > 3 || n < 0 || n > ctx->stream_len)
+        return fail(ctx, BGH_EINVAL, "bgh_debug_stream: bad argument");
+    BGH_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const void* src = which == 0 ? (const void*)ctx->d_xs : which == 1 ? (const void*)ctx->d_xw : which == 2 ? (const void*)ctx->d_xl : (const void*)ctx->d_gid;
+    BGH_CUDA(ctx, cudaMemcpy(out, src, (size_t)n * (which == 3 ? sizeof(int) : sizeof(double)), cudaMemcpyDeviceToHost));
+    return BGH_OK;
+}
+
 int bgh_debug_trace(bgh_ctx* ctx, int32_t enable, uint64_t* out, int64_t n_words)
 {
     if (!ctx) return BGH_EINVAL;
@@ -628,24 +681,15 @@ int bgh_upload(bgh_ctx* ctx, const float* chi2, const float* ld, const int32_t* 
     const int64_t Mp = pcnt[(size_t)G];
     if (Mp > 0x7fffff00LL) return fail(ctx, BGH_EINVAL, "bgh_upload: too many SNPs after padding");
     const int64_t Mpad = ((Mp + kChunk - 1) / kChunk) * kChunk + kChunk;
-    std::vector<float> s_sorted((size_t)Mpad, 0.0f), l_sorted((size_t)Mpad, 0.0f);   // l = 0 marks padding
     std::vector<int32_t> g_sorted((size_t)Mpad, G - 1);
     for (int32_t g = 0; g < G; ++g)
         for (int64_t j = pcnt[g]; j < pcnt[(size_t)g + 1]; ++j) g_sorted[(size_t)j] = g;
+    // stable destination of every SNP in the padded, gene-sorted stream (the scatter itself runs on the device)
+    std::vector<int32_t> dest((size_t)std::max<int64_t>(M, 1));
     {
         std::vector<int64_t> pos(pcnt.begin(), pcnt.end() - 1);
-        for (int64_t j = 0; j < M; ++j) {
-            const int32_t g = gene_id ? gene_id[j] : 0;
-            const int64_t d = pos[(size_t)g]++;
-            if (!(ld[j] > 0.0f) || !isfinite(ld[j]) || !isfinite(chi2[j]))
-                return fail(ctx, BGH_EINVAL, "bgh_upload: ld must be finite and > 0, chi2 finite (snps.py:121 gives l >= 1)");
-            s_sorted[(size_t)d] = chi2[j];
-            l_sorted[(size_t)d] = ld[j];
-        }
+        for (int64_t j = 0; j < M; ++j) dest[(size_t)j] = (int32_t)pos[(size_t)(gene_id ? gene_id[j] : 0)]++;
     }
-    double acc = 0.0;
-    for (int64_t j = 0; j < M; ++j) acc += log((double)ld[j]);
-    ctx->lik_const = -0.5 * acc - 0.5 * (double)M * kLog2Pi;
 
     const bool gw = ctx->cfg.model == BGH_MODEL_GW_NORMAL;
     const bool fp = gw ? true : ctx->cfg.first_gene_partial != 0;
@@ -718,16 +762,40 @@ int bgh_upload(bgh_ctx* ctx, const float* chi2, const float* ld, const int32_t* 
     BGH_CUDA(ctx, cudaMalloc(&ctx->d_split_ptr, sizeof(int) * (ns + 1)));
     BGH_CUDA(ctx, cudaMalloc(&ctx->d_split_slots, sizeof(int) * nsl));
     {
-        // prepared fp64 SoA: rho = sp - e wp - (c beta) lp is the standardised residual (bgh_lik_device.cuh)
-        std::vector<double> prep((size_t)Mpad);
-        for (int which = 0; which < 3; ++which) {
-            for (int64_t j = 0; j < Mpad; ++j) {
-                const double l = (double)l_sorted[(size_t)j], sq = sqrt(l);
-                prep[(size_t)j] = l > 0.0 ? (which == 0 ? (double)s_sorted[(size_t)j] / sq : (which == 1 ? 1.0 / sq : sq)) : 0.0;
-            }
-            double* dst = which == 0 ? ctx->d_xs : (which == 1 ? ctx->d_xw : ctx->d_xl);
-            BGH_CUDA(ctx, cudaMemcpy(dst, prep.data(), sizeof(double) * (size_t)Mpad, cudaMemcpyHostToDevice));
+        // prepared fp64 SoA: rho = sp - e wp - (c beta) lp is the standardised residual (bgh_lik_device.cuh); padding
+        // SNPs keep sp = wp = lp = 0.  Built by prepare_stream_kernel from the raw fp32 columns.
+        float *d_chi2 = nullptr, *d_ld = nullptr;
+        int *d_dest = nullptr, *d_bad = nullptr;
+        double* d_logp = nullptr;
+        const int n_blk = (int)std::min<int64_t>(1184, std::max<int64_t>(1, (M + kPrepThreads - 1) / kPrepThreads));
+        auto release = [&]() { cudaFree(d_chi2); cudaFree(d_ld); cudaFree(d_dest); cudaFree(d_bad); cudaFree(d_logp); };
+        cudaError_t e = cudaMalloc(&d_chi2, sizeof(float) * dest.size());
+        if (e == cudaSuccess) e = cudaMalloc(&d_ld, sizeof(float) * dest.size());
+        if (e == cudaSuccess) e = cudaMalloc(&d_dest, sizeof(int) * dest.size());
+        if (e == cudaSuccess) e = cudaMalloc(&d_bad, sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc(&d_logp, sizeof(double) * n_blk);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_chi2, chi2, sizeof(float) * (size_t)M, cudaMemcpyHostToDevice, 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_ld, ld, sizeof(float) * (size_t)M, cudaMemcpyHostToDevice, 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_dest, dest.data(), sizeof(int) * (size_t)M, cudaMemcpyHostToDevice, 0);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, sizeof(int), 0);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_xs, 0, sizeof(double) * (size_t)Mpad, 0);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_xw, 0, sizeof(double) * (size_t)Mpad, 0);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_xl, 0, sizeof(double) * (size_t)Mpad, 0);
+        std::vector<double> log_part((size_t)n_blk, 0.0);
+        int bad = 0;
+        if (e == cudaSuccess && M > 0) {
+            prepare_stream_kernel<<<n_blk, kPrepThreads>>>(d_chi2, d_ld, d_dest, (long long)M, ctx->d_xs, ctx->d_xw, ctx->d_xl, d_logp, d_bad);
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMemcpy(log_part.data(), d_logp, sizeof(double) * n_blk, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost);
         }
+        release();
+        BGH_CUDA(ctx, e);
+        if (bad) return fail(ctx, BGH_EINVAL, "bgh_upload: ld must be finite and > 0, chi2 finite (snps.py:121 gives l >= 1)");
+        double acc = 0.0;
+        for (int b = 0; b < n_blk; ++b) acc += log_part[(size_t)b];
+        ctx->lik_const = -0.5 * acc - 0.5 * (double)M * kLog2Pi;
+        ctx->stream_len = Mpad;
     }
     BGH_CUDA(ctx, cudaMemcpy(ctx->d_gid, g_sorted.data(), sizeof(int) * (size_t)Mpad, cudaMemcpyHostToDevice));
     BGH_CUDA(ctx, cudaMemcpy(ctx->d_groups, groups.data(), sizeof(int4) * groups.size(), cudaMemcpyHostToDevice));

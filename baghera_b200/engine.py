@@ -191,6 +191,16 @@ class Engine:
         check(self.L.bgh_get_partition(self.ctx, off.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), n), self.ctx)
         return off
 
+    def device_stream(self):
+        """The gene-sorted, padded stream bgh_upload built on the device: (s/sqrt(l), 1/sqrt(l), sqrt(l), gene id)."""
+        n = int(self.L.bgh_stream_len(self.ctx))
+        out = []
+        for which in range(4):
+            a = np.empty(n, dtype=np.int32 if which == 3 else np.float64)
+            check(self.L.bgh_debug_stream(self.ctx, which, a.ctypes.data_as(ctypes.c_void_p), n), self.ctx)
+            out.append(a)
+        return tuple(out)
+
     @property
     def n_split_genes(self):
         return int(self.L.bgh_n_split_genes(self.ctx))

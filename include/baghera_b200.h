@@ -166,6 +166,11 @@ int bgh_from_device_layout(bgh_ctx* ctx, const double* x_dc, double* x_cd, void*
 int32_t bgh_n_groups(const bgh_ctx* ctx);
 int bgh_get_partition(const bgh_ctx* ctx, int32_t* offsets, int32_t n);
 int32_t bgh_n_split_genes(const bgh_ctx* ctx);
+/* Introspection for tests: the gene-sorted, padded stream bgh_upload built on the device.  which = 0 / 1 / 2:
+ * s/sqrt(l), 1/sqrt(l), sqrt(l) as double[n]; which = 3: compact gene id per position as int32[n].
+ * bgh_stream_len = padded length (every gene a multiple of the kernel's batch of 8 SNPs, plus chunk slack). */
+int64_t bgh_stream_len(const bgh_ctx* ctx);
+int bgh_debug_stream(bgh_ctx* ctx, int32_t which, void* out, int64_t n);
 int64_t bgh_launch_count(const bgh_ctx* ctx);
 /* average device time (ms) of the likelihood kernel since the last call with reset != 0; timing is
  * only collected after bgh_set_profiling(ctx, 1) (adds CUDA events around each launch). */

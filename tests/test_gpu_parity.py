@@ -281,3 +281,50 @@ def test_gamma_model_at_full_size():
         assert abs(lp[i] - lp_ref[k]) <= REL_TOL * abs(lp_ref[k])
         assert grad_rel_err(g[i], g_ref[k]) <= REL_TOL
     eng.close()
+
+
+@pytest.mark.parametrize("M,G", [(20_000, 200), (1_100_000, 15_000), (37, 5)])
+def test_device_built_stream_is_the_stable_gene_sort(M, G):
+    """bgh_upload builds the sorted / padded / prepared fp64 stream on the device (prepare_stream_kernel): every bit
+    must equal the host formulas on a STABLE sort by gene id (file order kept inside a gene, ref: Q6), every gene
+    padded to a multiple of 8 zero-weight SNPs, and the likelihood constant -0.5 sum log(2 pi l)."""
+    d = synth.make_arrays(M, G, seed=5)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(M)                      # file order is not gene order
+    chi2, ld, gid = d.chi2[perm], d.ld[perm], d.gene_id[perm]
+    from baghera_b200.engine import Engine
+    eng = Engine(chi2, ld, gid, d.G, d.c, 4)
+    sp, wp, lp, g_dev = eng.device_stream()
+    order = np.argsort(gid, kind="stable")
+    cnt = np.bincount(gid, minlength=d.G)
+    pcnt = np.concatenate([[0], np.cumsum((cnt + 7) // 8 * 8)])
+    start = np.concatenate([[0], np.cumsum(cnt)])[:-1]
+    gs = gid[order]
+    dest = pcnt[gs] + (np.arange(M) - start[gs])
+    l = ld[order].astype(np.float64)
+    sq = np.sqrt(l)
+    ref = np.zeros((3, sp.size))
+    ref[0, dest] = chi2[order].astype(np.float64) / sq
+    ref[1, dest] = 1.0 / sq
+    ref[2, dest] = sq
+    assert np.array_equal(sp, ref[0]) and np.array_equal(wp, ref[1]) and np.array_equal(lp, ref[2])
+    Mp = int(pcnt[-1])
+    assert np.array_equal(g_dev[:Mp], np.repeat(np.arange(d.G), np.diff(pcnt)))
+    ref_const = -0.5 * np.sum(np.log(ld.astype(np.float64))) - 0.5 * M * np.log(2 * np.pi)
+    assert abs(eng.lik_const - ref_const) <= 1e-13 * abs(ref_const)
+    eng.close()
+
+
+def test_upload_rejects_bad_ld():
+    """ld <= 0 or non-finite inputs are refused by the device-side validation (BGH_EINVAL), not silently used."""
+    from baghera_b200.engine import Engine
+    from baghera_b200._lib import BghError
+    d = synth.make_arrays(2_000, 20, seed=6)
+    ld = d.ld.copy()
+    ld[1234] = 0.0
+    with pytest.raises(BghError):
+        Engine(d.chi2, ld, d.gene_id, d.G, d.c, 4)
+    chi2 = d.chi2.copy()
+    chi2[7] = np.nan
+    with pytest.raises(BghError):
+        Engine(chi2, d.ld, d.gene_id, d.G, d.c, 4)
