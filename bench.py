@@ -405,6 +405,18 @@ def bench_gpu(args, wl):
         fp64 = {"achieved_ginstr_s": dp_instr / (step_ms * 1e-3) / 1e9, "peak_ginstr_s": dfma_peak,
                 "unit": "G FP64 lane-instr/s", "frac": (dp_instr / (step_ms * 1e-3) / 1e9 / dfma_peak) if dfma_peak else None,
                 "peak_source": "bgh_dfma_peak microbenchmark, same process", "dp_instr_per_launch": dp_instr}
+        # register-file ceiling of the built kernel's hot loop (a DFMA that reads three fresh operands takes 3 pipe
+        # cycles instead of 2): static analysis of the SASS of the library that just ran
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from sass_dfma_reads import kernel_ceiling
+            cl, cpl = (eng.Cp, 1) if eng.Cp <= 32 else (32, 2)
+            gam = 1 if model == "gamma" else 0
+            mangled = ("_ZN3bgh23logp_grad_chainx_kernelILi%dELi%dELb%dEEEvNS_11Eval2ParamsE" if world > 1 else
+                       "_ZN3bgh22logp_grad_fused_kernelILi%dELi%dELb%dEEEvNS_11FusedParamsE") % (cl, cpl, gam)
+            fp64["rf_ceiling"] = kernel_ceiling(os.path.join(ROOT, "baghera_b200", "libbaghera_b200.so"), mangled)
+        except Exception:
+            fp64["rf_ceiling"] = None
         return roofline, fp64
 
     Q = synth.jittered_start(D, C, seed=1, model=model)           # the same chains at every N

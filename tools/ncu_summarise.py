@@ -1,6 +1,7 @@
-"""Condenses `ncu --page raw --csv` exports (gpurun_out/prof_r2_*_raw.csv) into profiles/: one small CSV per capture with the
+"""Condenses `ncu --page raw --csv` exports (gpurun_out/prof_<round>_*_raw.csv) into profiles/: one small CSV per capture with the
 metrics DESIGN.md quotes, and profiles/ncu_traffic.json (DRAM bytes per launch, read by bench.py for roofline.traffic)."""
 import csv, glob, json, os, sys
+RND = sys.argv[1] if len(sys.argv) > 1 else "r3"      # capture round: gpurun_out/prof_<RND>_*_raw.csv -> profiles/<RND>_*
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -15,13 +16,13 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 traffic_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
 traffic = json.load(open(traffic_path))
 keymap = {"lik_cfg3": "cfg3:1", "lik_cfg2": "cfg2:1", "lik_cfg5": "cfg5:1", "lik_cfg3sh": "cfg3:sharded-kernel-one-rank"}
-for path in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_r2_*_raw.csv"))):
+for path in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_%s_*_raw.csv" % RND))):
     rows = list(csv.reader(open(path)))
     if len(rows) < 3:
         print("skip", path); continue
     hdr, units, vals = rows[0], rows[1], rows[2]
-    name = os.path.basename(path)[len("prof_r2_"):-len("_raw.csv")]
-    out = os.path.join(ROOT, "profiles", "r2_%s_ncu_full_summary.csv" % name)
+    name = os.path.basename(path)[len("prof_%s_" % RND):-len("_raw.csv")]
+    out = os.path.join(ROOT, "profiles", "%s_%s_ncu_full_summary.csv" % (RND, name))
     with open(out, "w", newline="") as f:
         w = csv.writer(f)
         w.writerow(["metric", "unit", "value"])
@@ -40,8 +41,8 @@ for path in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_r2_*_raw.csv
           vals[hdr.index("lts__t_sector_hit_rate.pct")]))
     if name in keymap:
         traffic[keymap[name]] = {"kernel": vals[hdr.index("Kernel Name")], "dram_read_bytes": int(rd), "dram_write_bytes": int(wr),
-                                 "source": "profiles/r2_%s_ncu_full_summary.csv" % name}
+                                 "source": "profiles/%s_%s_ncu_full_summary.csv" % (RND, name)}
     elif name.startswith("tick"):
         traffic["sampler-%s:1" % name] = {"kernel": vals[hdr.index("Kernel Name")], "dram_read_bytes": int(rd), "dram_write_bytes": int(wr),
-                                          "note": "one launch = up to 64 ticks (leapfrogs of all 64 chains)", "source": "profiles/r2_%s_ncu_full_summary.csv" % name}
+                                          "note": "one launch = up to 64 ticks (leapfrogs of all 64 chains)", "source": "profiles/%s_%s_ncu_full_summary.csv" % (RND, name)}
 json.dump(traffic, open(traffic_path, "w"), indent=1)

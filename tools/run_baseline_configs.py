@@ -1,5 +1,5 @@
 """Runs BASELINE.json's configurations 1-3 through the reference-facing CLI (`baghera-tool gene-heritability`) on synthetic
-annotated-SNP tables of the named shapes and records what the sampler did (profiles/r2_baseline_configs.json).
+annotated-SNP tables of the named shapes and records what the sampler did (profiles/r3_baseline_configs_cli.json).
 
     python tools/run_baseline_configs.py [cfg1 cfg2 cfg3]
 
@@ -55,4 +55,4 @@ for name in which:
     }
     print(name, json.dumps(out[name]), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open("gpurun_out/r2_baseline_configs.json", "w"), indent=1)
+json.dump(out, open("gpurun_out/r3_baseline_configs.json", "w"), indent=1)

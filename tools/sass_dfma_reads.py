@@ -31,6 +31,30 @@ def analyse(lines):
     return n, reads_tot, cost, hist
 
 
+def hot_loop(lines):
+    """The branch-free stretch with the most DFMAs of a function's SASS lines."""
+    best, cur = [], []
+    for l in lines + ["BRA"]:
+        if re.search(r"\b(BRA|EXIT|RET|CALL|BSYNC|WARPSYNC)\b", l):
+            if sum("DFMA" in x for x in cur) > sum("DFMA" in x for x in best):
+                best = cur
+            cur = []
+        else:
+            cur.append(l)
+    return best
+
+
+def kernel_ceiling(so_path, mangled):
+    """Issue ceiling (fraction of the DFMA peak) of the hot loop of one kernel of a built library, or None."""
+    import subprocess
+    try:
+        out = subprocess.run(["cuobjdump", "-sass", "-fun", mangled, so_path], capture_output=True, text=True, timeout=60).stdout
+    except Exception:
+        return None
+    n, r, c, h = analyse(hot_loop(out.splitlines()))
+    return {"dfma_in_hot_loop": n, "three_operand_reads": h.get(3, 0), "frac_of_dfma_peak": 2.0 * n / c} if n >= 16 else None
+
+
 if __name__ == "__main__":
     src = open(sys.argv[1]).read().splitlines()
     if len(sys.argv) > 3:
