@@ -1164,23 +1164,27 @@ __device__ __forceinline__ void tick2_scalar(const Tick2Params& t, unsigned char
 #pragma unroll 1
         for (int j = 1; j < kAsyncPartials; ++j)
             if ((u_acc >> j) & 1u) acc[j * kAs] = 0.0;
-        // fixed-order CTA sum of the used quantities of acc[] into s.sum (xor tree inside the warp, then the warps in order)
+        // fixed-order CTA sum of the used quantities of acc[] into s.sum,
+        // the quantities in parallel: warp w sums quantities w and w + 16 over the 512 per-thread slots (lane-strided in a fixed
+        // order, then an xor tree) — one pass for all used quantities instead of a shuffle tree per quantity in sequence
+        // (a deep tree check uses 23 of them: that sequence was the tail of the slowest chain's scalar phase)
         auto reduce_acc = [&]() {
             const unsigned u = u_acc;
+            acc[0] = kin;
+            __syncthreads();
 #pragma unroll 1
-            for (int j = 0; j < kAsyncPartials; ++j) {
+            for (int j = warp; j < kAsyncPartials; j += kLikWarps) {
                 if (!((u >> j) & 1u)) continue;
-                double x = j == 0 ? kin : acc[j * kAs];
+                const double* const src = s.sr + kLikThreads + (size_t)j * kAs;
+                double v[kLikThreads / 32];
+#pragma unroll
+                for (int k = 0; k < kLikThreads / 32; ++k) v[k] = src[lane + 32 * k];
+                double x = 0.0;
+#pragma unroll
+                for (int k = 0; k < kLikThreads / 32; ++k) x += v[k];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-                if (lane == 0) s.red2[warp * kAsyncPartials + j] = x;
-            }
-            __syncthreads();
-            if (tid < kAsyncPartials && ((u >> tid) & 1u)) {
-                double tsum = 0.0;
-#pragma unroll
-                for (int w = 0; w < kLikWarps; ++w) tsum += s.red2[w * kAsyncPartials + tid];
-                s.sum[kT2Lik + tid] += tsum;
+                if (lane == 0) s.sum[kT2Lik + j] += x;
             }
             __syncthreads();
             kin = 0.0;
@@ -1588,7 +1592,7 @@ __global__ void __launch_bounds__(kLikThreads, 1) nuts_tick2_kernel(const __grid
         fence_proxy_async();   // the staging area was written through the generic proxy (scalar phase, accumulators)
         for (int cb = 0; cb < t.chain_blocks; ++cb) lik_phase<CL, CPL, GAMMA>(t.lik, smem_raw, blockIdx.x, cb, par);
         if (tr) tr[9] = global_timer_ns();
-        tick2_post<(CL * CPL < 64)>(t, own, s_bits, s_h, s_kin0c, s_need, smem_raw);
+        tick2_post<true>(t, own, s_bits, s_h, s_kin0c, s_need, smem_raw);
         if (tr) tr[1] = global_timer_ns();
         grid_barrier(t.bar, target, t.status);
         if (tr) tr[2] = global_timer_ns();
