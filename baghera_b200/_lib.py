@@ -118,6 +118,7 @@ SIGNATURES = {
     "bgh_from_device_layout": (_i32, [_vp, _vp, _vp, _vp]),
     "bgh_n_groups": (_i32, [_vp]),
     "bgh_get_partition": (_i32, [_vp, _pi32, _i32]),
+    "bgh_get_sampler_partition": (_i32, [_vp, _pi32, _i32]),
     "bgh_n_split_genes": (_i32, [_vp]),
     "bgh_stream_len": (_i64, [_vp]),
     "bgh_debug_stream": (_i32, [_vp, _i32, _vp, _i64]),

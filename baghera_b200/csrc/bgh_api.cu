@@ -30,7 +30,7 @@ static double plan_snap()
 
 int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_cta, int groups_per_cta,
                bool first_partial, bool last_partial, int first_row, int last_row, double kappa,
-               Plan* plan, std::string* err, int align, int n_replicated, bool owns_replicated, double snap)
+               Plan* plan, std::string* err, int align, int n_replicated, bool owns_replicated, double snap, double kappa_warp)
 {
     const int n_groups = n_cta * groups_per_cta;
     if (M < 0 || M > 0x7fffff00LL || n_cta <= 0 || groups_per_cta <= 0 || G <= 0) {
@@ -176,14 +176,33 @@ int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_cta, int groups_p
                 const int64_t ng_started = std::lower_bound(goff.begin() + r.g0, goff.begin() + r.g1, (int32_t)x) - (goff.begin() + r.g0);
                 return (double)(x - r.a) + kappa * (double)ng_started;
             };
+            // Two-level cuts (kappa_warp >= 0, the sampler plan): the CTA cuts equalise SNPs + kappa * genes (a gene also costs
+            // the leapfrog of its row, which ALL threads of the CTA share), the cuts between the warps of a CTA equalise
+            // SNPs + kappa_warp * genes (what a boundary costs inside the likelihood pass) — with one kappa for both a warp
+            // holding one long gene streams three times the SNPs of a warp holding six short ones and the CTA waits for it.
+            const bool two_level = kappa_warp >= 0.0 && kappa_warp != kappa;
+            int64_t cta_a = r.a, cta_b = r.b;      // span of the CTA being cut (two-level)
+            double cta_w = 0.0;
+            auto started = [&](int64_t x) {
+                return (int64_t)(std::lower_bound(goff.begin() + r.g0, goff.begin() + r.g1, (int32_t)x) - (goff.begin() + r.g0));
+            };
             for (int k = 0; k < ng; ++k) {
                 int64_t x;
-                {
+                if (!two_level || k % groups_per_cta == 0) {
                     const double target = r.w * (double)k / (double)ng;
                     int64_t lo = r.a, hi = r.b;
                     while (lo < hi) {
                         const int64_t mid = lo + (hi - lo) / 2;
                         if (cost(mid) < target) lo = mid + 1; else hi = mid;
+                    }
+                    x = lo;
+                } else {
+                    const double target = cta_w * (double)(k % groups_per_cta) / (double)groups_per_cta;
+                    const int64_t s0 = started(cta_a);
+                    int64_t lo = cta_a, hi = cta_b;
+                    while (lo < hi) {
+                        const int64_t mid = lo + (hi - lo) / 2;
+                        if ((double)(mid - cta_a) + kappa_warp * (double)(started(mid) - s0) < target) lo = mid + 1; else hi = mid;
                     }
                     x = lo;
                 }
@@ -202,6 +221,21 @@ int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_cta, int groups_p
                 }
                 P.off[(size_t)(v0 + k)] = (int32_t)x;
                 prev = x;
+                if (two_level && k % groups_per_cta == 0) {
+                    // the CTA's span ends at the (unsnapped) ideal cut of the next CTA: close enough for the warp targets
+                    cta_a = x;
+                    if (k + groups_per_cta >= ng) cta_b = r.b;
+                    else {
+                        const double target = r.w * (double)(k + groups_per_cta) / (double)ng;
+                        int64_t lo = r.a, hi = r.b;
+                        while (lo < hi) {
+                            const int64_t mid = lo + (hi - lo) / 2;
+                            if (cost(mid) < target) lo = mid + 1; else hi = mid;
+                        }
+                        cta_b = std::max(lo, cta_a);
+                    }
+                    cta_w = (double)(cta_b - cta_a) + kappa_warp * (double)(started(cta_b) - started(cta_a));
+                }
             }
         }
         v0 += ng;
@@ -592,6 +626,15 @@ int bgh_get_partition(const bgh_ctx* ctx, int32_t* offsets, int32_t n)
     return BGH_OK;
 }
 
+int bgh_get_sampler_partition(const bgh_ctx* ctx, int32_t* offsets, int32_t n)
+{
+    if (!ctx || !offsets) return BGH_EINVAL;
+    if (!ctx->uploaded) return BGH_ESTATE;
+    if (n != ctx->n_groups + 1) return BGH_EINVAL;
+    memcpy(offsets, ctx->plan2.off.data(), sizeof(int32_t) * (size_t)n);
+    return BGH_OK;
+}
+
 // Host-only planning entry point used by the CPU tests (no device needed): sorted gene ids in,
 // offsets[n_groups+1], flags[n_groups] out; split CSR returned through caller-sized buffers.
 int bgh_debug_plan(int64_t M, const int32_t* gid_sorted, int32_t G, int32_t n_cta, int32_t groups_per_cta, int32_t first_partial,
@@ -703,9 +746,10 @@ int bgh_upload(bgh_ctx* ctx, const float* chi2, const float* ld, const int32_t* 
     {
         const char* ek = getenv("BGH_NUTS_KAPPA");
         const char* es = getenv("BGH_NUTS_SNAP");
+        const char* ew = getenv("BGH_NUTS_KAPPA_WARP");
         rc = build_plan(Mp, g_sorted.data(), G, ctx->n_cta, kLikWarps, fp, lp, ctx->cfg.first_gene_row,
                         ctx->cfg.last_gene_row, (ek && *ek) ? atof(ek) : 60.0, &ctx->plan2, &err, kLikBatch, ctx->cfg.n_replicated,
-                        ctx->cfg.owns_replicated != 0, (es && *es) ? atof(es) : 0.5);
+                        ctx->cfg.owns_replicated != 0, (es && *es) ? atof(es) : 0.5, (ew && *ew) ? atof(ew) : 8.0);
         if (rc != BGH_OK) return fail(ctx, rc, err);
     }
     // rows each CTA owns in the fused sampler kernel (bgh_tick2.cu): genes complete inside one SNP range of the CTA
@@ -1546,6 +1590,10 @@ static int nuts_run_tick2(bgh_ctx* ctx, const bgh_nuts_async_buffers* buf, const
     fill_ll_peer(ctx, true, &t.peer);
     t.peer.epoch_base = ctx->t2_epoch;
     t.phase_trace = ctx->d_trace;   // NULL unless bgh_debug_trace enabled it (tools/time_tick2.py)
+    if (ctx->d_trace && getenv("BGH_T2_LIK_TRACE")) {   // tools: the per-warp stamps of the likelihood pass (last tick) instead
+        t.lik.trace = ctx->d_trace;
+        t.phase_trace = nullptr;
+    }
     if (ctx->d_trace)               // the evaluation kernels share the buffer (per-warp stamps): start from zeros
         BGH_CUDA(ctx, cudaMemsetAsync(ctx->d_trace, 0, sizeof(unsigned long long) * (size_t)ctx->chain_blocks * ctx->n_cta * kLikWarps * 8, s));
 

@@ -51,7 +51,8 @@ struct Plan {
 // (the upload pads every gene to a multiple of the kernel's batch, so gene boundaries already are).
 int build_plan(int64_t M, const int32_t* gid, int32_t G, int n_cta, int groups_per_cta,
                bool first_partial, bool last_partial, int first_row, int last_row, double kappa,
-               Plan* plan, std::string* err, int align = 1, int n_replicated = 0, bool owns_replicated = true, double snap = 0.0);
+               Plan* plan, std::string* err, int align = 1, int n_replicated = 0, bool owns_replicated = true, double snap = 0.0,
+               double kappa_warp = -1.0);   // >= 0: the cuts between the warps of a CTA use this boundary cost (sampler plan)
 
 struct LikParams {
     const double* sp;     // prepared SoA, gene sorted: s / sqrt(l)

@@ -185,10 +185,12 @@ class Engine:
         self.lik_const = float(total)
 
     # ------------------------------------------------------------------ introspection
-    def partition(self):
+    def partition(self, sampler=False):
+        """SNP-range offsets (n_groups + 1) of the evaluation plan, or of the sampler kernel's plan."""
         n = int(self.L.bgh_n_groups(self.ctx)) + 1
         off = np.empty(n, dtype=np.int32)
-        check(self.L.bgh_get_partition(self.ctx, off.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), n), self.ctx)
+        fn = self.L.bgh_get_sampler_partition if sampler else self.L.bgh_get_partition
+        check(fn(self.ctx, off.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), n), self.ctx)
         return off
 
     def device_stream(self):

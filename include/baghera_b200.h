@@ -165,6 +165,9 @@ int bgh_from_device_layout(bgh_ctx* ctx, const double* x_dc, double* x_cd, void*
  * array) and kernel launch counters (how many of this library's kernels were launched). */
 int32_t bgh_n_groups(const bgh_ctx* ctx);
 int bgh_get_partition(const bgh_ctx* ctx, int32_t* offsets, int32_t n);
+/* the same for the sampler kernel's own work plan (bgh_nuts_run): CTA cuts weigh a gene by the leapfrog of its row,
+ * the cuts between the warps of a CTA by what a gene boundary costs inside the likelihood pass */
+int bgh_get_sampler_partition(const bgh_ctx* ctx, int32_t* offsets, int32_t n);
 int32_t bgh_n_split_genes(const bgh_ctx* ctx);
 /* Introspection for tests: the gene-sorted, padded stream bgh_upload built on the device.  which = 0 / 1 / 2:
  * s/sqrt(l), 1/sqrt(l), sqrt(l) as double[n]; which = 3: compact gene id per position as int32[n].
