@@ -136,6 +136,7 @@ SIGNATURES = {
     "bgh_nuts_run": (_i32, [_vp, ctypes.POINTER(bgh_nuts_async_buffers), ctypes.POINTER(bgh_nuts_cfg), _i32, _i32, _i32,
                             _vp, _pi64]),
     "bgh_debug_trace": (_i32, [_vp, _i32, _vp, _i64]),
+    "bgh_debug_sampler_plan": (_i32, [_i64, _pi32, _i32, _i32, _i32, _i32, _pi32, _pi32]),
     "bgh_csv_read": (_i32, [ctypes.c_char_p, _i32, _i32, ctypes.POINTER(_vp)]),
     "bgh_ingest_last_error": (ctypes.c_char_p, []),
     "bgh_table_rows": (_i64, [_vp]),

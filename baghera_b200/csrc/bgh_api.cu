@@ -658,6 +658,20 @@ int bgh_debug_plan(int64_t M, const int32_t* gid_sorted, int32_t G, int32_t n_ct
     return BGH_OK;
 }
 
+// The sampler kernel's plan (defaults of bgh_upload: kappa 60, snap 0.5, kappa_warp 8, ranges aligned to the batch) on the host.
+int bgh_debug_sampler_plan(int64_t M, const int32_t* gid_sorted, int32_t G, int32_t n_cta, int32_t groups_per_cta, int32_t two_level,
+                           int32_t* offsets, int32_t* flags)
+{
+    Plan P;
+    std::string err;
+    int rc = build_plan(M, gid_sorted, G, n_cta, groups_per_cta, false, false, -1, -1, 60.0, &P, &err, kLikBatch, 0, true, 0.5,
+                        two_level ? 8.0 : -1.0);
+    if (rc != BGH_OK) return fail(nullptr, rc, err);
+    memcpy(offsets, P.off.data(), sizeof(int32_t) * P.off.size());
+    memcpy(flags, P.flags.data(), sizeof(int32_t) * P.flags.size());
+    return BGH_OK;
+}
+
 // Tools only: enable (buf != NULL -> allocate) per-warp phase timestamps of the likelihood kernel and
 // copy the last launch's trace [chain_blocks * n_cta * 16 warps][8] u64 to `out` (may be NULL).
 int64_t bgh_stream_len(const bgh_ctx* ctx) { return (ctx && ctx->uploaded) ? ctx->stream_len : 0; }

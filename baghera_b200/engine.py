@@ -246,3 +246,16 @@ def debug_plan(gid_sorted, G, n_cta, groups_per_cta=16, first_partial=False, las
     n = ns.value
     return dict(off=off, flags=flags, n_cta=n_cta, groups_per_cta=groups_per_cta, split_gene=sg[:n].copy(), split_ptr=sp[:n + 1].copy(),
                 split_slots=ss[:sp[n]].copy())
+
+
+def debug_sampler_plan(gid_sorted, G, n_cta, groups_per_cta=16, two_level=True):
+    """Host-only sampler work plan (bgh_upload's defaults): returns (offsets[n_groups + 1], flags[n_groups])."""
+    n_groups = n_cta * groups_per_cta
+    L = _lib.lib()
+    gid = np.ascontiguousarray(gid_sorted, dtype=np.int32)
+    off = np.zeros(n_groups + 1, np.int32)
+    flags = np.zeros(n_groups, np.int32)
+    P = ctypes.POINTER(ctypes.c_int32)
+    check(L.bgh_debug_sampler_plan(gid.shape[0], gid.ctypes.data_as(P), int(G), int(n_cta), int(groups_per_cta), int(bool(two_level)),
+                                   off.ctypes.data_as(P), flags.ctypes.data_as(P)))
+    return off, flags

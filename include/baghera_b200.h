@@ -315,6 +315,11 @@ typedef struct bgh_nuts_async_buffers {
 int bgh_nuts_run(bgh_ctx* ctx, const bgh_nuts_async_buffers* buf, const bgh_nuts_cfg* cfg, int32_t tune,
                  int32_t draws, int32_t poll_ticks, void* stream, int64_t* n_ticks);
 
+/* Host-only: the sampler kernel's work plan with bgh_upload's defaults (gid_sorted padded to the batch of 8 as on the
+ * device); two_level = 0 cuts the warps of a CTA with the CTA-level boundary cost as well (round-2 behaviour, for tests). */
+int bgh_debug_sampler_plan(int64_t M, const int32_t* gid_sorted, int32_t G, int32_t n_cta, int32_t groups_per_cta, int32_t two_level,
+                           int32_t* offsets, int32_t* flags);
+
 /* Tools only: per-warp phase timestamps (globaltimer ns) of the likelihood kernel.  enable != 0
  * allocates the trace buffer; out (optional) receives the last launch's
  * [chain_blocks * n_cta * 16][8] u64 words {t_enter, t_setup_done, t_stream_done, t_barrier,

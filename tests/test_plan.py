@@ -74,3 +74,29 @@ def test_plan_rejects_bad_input(built_lib):
         debug_plan(np.array([0, 0, 2], np.int32), 3, 2, 4)      # gene 1 missing
     with pytest.raises(BghError):
         debug_plan(np.array([0, 5], np.int32), 3, 2, 4)         # id out of range
+
+
+def test_sampler_plan_balances_the_warps_of_a_cta_by_likelihood_cost(built_lib):
+    """Sampler plan (bgh_tick2.cu): CTA cuts weigh a gene by the leapfrog of its row (kappa 60), but the cuts between the
+    WARPS of a CTA must balance what the likelihood pass costs a warp (SNPs + ~8 per gene boundary): the CTA waits for its
+    slowest warp.  With one kappa for both levels a warp holding one long gene streamed ~3x the mean."""
+    from baghera_b200.engine import debug_sampler_plan
+    d = synth.make_arrays(550_000, 7_500, seed=3)            # the shape of a rank of a 2-way gene-block sharding
+    cnt = np.bincount(d.gene_id, minlength=d.G)
+    gid = np.repeat(np.arange(d.G, dtype=np.int32), (cnt + 7) // 8 * 8)      # padded to the batch, as on the device
+    res = {}
+    for two_level in (True, False):
+        off, flags = debug_sampler_plan(gid, d.G, 148, 16, two_level)
+        assert off[0] == 0 and off[-1] == gid.shape[0] and np.all(np.diff(off) >= 0) and np.all(off[1:-1] % 8 == 0)
+        worst = []
+        for c in range(148):
+            if flags[c * 16] & 4:          # exclusive CTA (one huge gene): equal cuts
+                continue
+            cost = []
+            for v in range(c * 16, c * 16 + 16):
+                a, b = off[v], off[v + 1]
+                cost.append((b - a) + 8.0 * (len(np.unique(gid[a:b])) if b > a else 0))
+            cost = np.array(cost)
+            worst.append(cost.max() / cost.mean())
+        res[two_level] = (np.median(worst), np.max(worst))
+    assert res[True][0] < 1.45 and res[True][0] < 0.9 * res[False][0] and res[True][1] < 0.85 * res[False][1], res
