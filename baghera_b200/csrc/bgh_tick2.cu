@@ -260,6 +260,7 @@ __device__ __forceinline__ unsigned used_quantities(int bits)
 // are in flight per thread.
 // ---------------------------------------------------------------------------------------------
 constexpr int kUPre = 8, kUPost = 4;
+static_assert(kUPost % 2 == 0, "the level-major POST pass takes the rows of a batch in pairs");
 
 struct T2Own {
     const int* rows;     // gene ids of the CTA's rows (shared memory, or global when the list is too long)
