@@ -1111,7 +1111,13 @@ __device__ __forceinline__ void tick2_scalar(const Tick2Params& t, unsigned char
         FinParams fc = f;                                // closing formulas: the chain's working buffer
         fc.q = f.q + wo;
         fc.grad = f.grad + wo;
-        const ChainConst cc = chain_const(fc, c);        // every thread: cheap, avoids a broadcast
+        // the chain's closing constants (two exp / log1p chains on the FP64 pipe, needed by thread 0 only, in part C): ONE thread
+        // of the warp with the lightest reduction duty computes them under the loads of part A and hands them over in shared
+        // memory (all 16 warps computing them cost ~1.5 us of this latency-bound phase)
+        if (tid == kLikThreads - 32) {
+            const ChainConst k = chain_const(fc, c);
+            s.red2[0] = k.iW; s.red2[1] = k.iW2; s.red2[2] = k.mi; s.red2[3] = k.lp0; s.red2[4] = k.x0; s.red2[5] = k.x1;
+        }
         GeneCoef gc;
         gc.iW2 = gc.mi = gc.beta = 0.0;
         const int k_split = (!gw && d >= t.row0) ? tid - t.row0 : (gw && tid == 1 ? 0 : -1);     // split-gene index of this thread's row
@@ -1219,6 +1225,8 @@ __device__ __forceinline__ void tick2_scalar(const Tick2Params& t, unsigned char
             ChainSums cs;
             cs.A_ll = s.sum[0]; cs.A_e = s.sum[1]; cs.S1 = s.sum[2]; cs.S2 = s.sum[3];
             double lp, g[3];
+            ChainConst cc;
+            cc.iW = s.red2[0]; cc.iW2 = s.red2[1]; cc.mi = s.red2[2]; cc.lp0 = s.red2[3]; cc.x0 = s.red2[4]; cc.x1 = s.red2[5];
             chain_closing(fc, c, cs, cc, lp, g);
             f.logp[c] = lp;
             s_hg[0] = g[0]; s_hg[1] = g[1]; s_hg[2] = g[2]; s_hg[3] = lp;
