@@ -624,11 +624,12 @@ __device__ __forceinline__ void split_gene_sums(const FinParams& f, int c, doubl
 }
 
 // the same sums with the (constant) slot lists cached in shared memory: one global round trip instead of three
-__device__ __forceinline__ void split_gene_sums_cached(const FinParams& f, int c, double* s_sr, const int* s_sptr, const int* s_sidx)
+// (k_first: first short-list gene the per-thread loop still has to sum; the caller may have done one gene per thread itself)
+__device__ __forceinline__ void split_gene_sums_cached(const FinParams& f, int c, double* s_sr, const int* s_sptr, const int* s_sidx, int k_first)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Cp = f.Cp;
-    for (int k = f.n_long + tid; k < f.n_split; k += blockDim.x) {
+    for (int k = k_first + tid; k < f.n_split; k += blockDim.x) {
         const int s0 = s_sptr[k], n = s_sptr[k + 1] - s0;
         double tot = 0.0;
         for (int i = 0; i < n; ++i) tot += f.slots[(size_t)s_sidx[s0 + i] * Cp + c];
@@ -1090,8 +1091,18 @@ __device__ __forceinline__ void tick2_scalar(const Tick2Params& t, unsigned char
         const unsigned used = used_quantities(bits_old);
         const int nl = (bits_old >> kCbNLvlShift) & 15, lm = (bits_old >> kCbLvlMinShift) & 15;
         // ---- A: everything this phase reads from global memory is requested now
-        if (tid < kAscCount) s.sc[tid] = sc(p, tid, c);
-        if (tid >= 32 && tid < 32 + kAfCount) s.fl[tid - 32] = t2_afl(a, tid - 32, c);
+        // (a warp issues in order: a load whose value is STORED right away would hold back every later load of the warp by a
+        // round trip, so the per-chain scalars / flags and the first slots of the thread's split gene are only loaded here and
+        // consumed after the partial sums' loads have been issued)
+        const double sc_v = tid < kAscCount ? sc(p, tid, c) : 0.0;
+        const int fl_v = (tid >= 32 && tid < 32 + kAfCount) ? t2_afl(a, tid - 32, c) : 0;
+        constexpr int kSlotsAhead = 4;
+        double sv[kSlotsAhead];
+        const int k_mine = f.n_long + tid;
+        const bool slots_mine = split_cached && k_mine < f.n_split;
+        const int sl0 = slots_mine ? s_sptr[k_mine] : 0, sln = slots_mine ? s_sptr[k_mine + 1] - sl0 : 0;
+#pragma unroll
+        for (int j = 0; j < kSlotsAhead; ++j) sv[j] = j < sln ? f.slots[(size_t)s_sidx[sl0 + j] * p.Cp + c] : 0.0;
         const bool has_row = tid < n_late;
         const int lr = has_row ? s_lrow[tid] : 0;
         const int d = lr & (kLateRep - 1);
@@ -1141,6 +1152,10 @@ __device__ __forceinline__ void tick2_scalar(const Tick2Params& t, unsigned char
                     v[j] = (on0 && row < f.n_cta) ? src0[(size_t)row * st0] : 0.0;
                     w[j] = (on1 && row < f.n_cta) ? src1[(size_t)row * st1] : 0.0;
                 }
+                if (i0 == 0) {      // every load of part A is in flight: hand over the early ones
+                    if (tid < kAscCount) s.sc[tid] = sc_v;
+                    if (tid >= 32 && tid < 32 + kAfCount) s.fl[tid - 32] = fl_v;
+                }
                 a0 += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
                 a1 += ((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]));
             }
@@ -1154,8 +1169,19 @@ __device__ __forceinline__ void tick2_scalar(const Tick2Params& t, unsigned char
                 if (k1 < kT2Nq) s.sum[k1] = a1;
             }
         }
-        if (split_cached) split_gene_sums_cached(f, c, s.sr, s_sptr, s_sidx);
-        else         split_gene_sums(f, c, s.sr);
+        if (split_cached) {
+            if (slots_mine) {      // the slots in list order, as split_gene_sums_cached adds them
+                double tot = 0.0;
+#pragma unroll
+                for (int j = 0; j < kSlotsAhead; ++j)
+                    if (j < sln) tot += sv[j];
+                for (int j = kSlotsAhead; j < sln; ++j) tot += f.slots[(size_t)s_sidx[sl0 + j] * p.Cp + c];
+                s.sr[k_mine] = tot;
+            }
+            split_gene_sums_cached(f, c, s.sr, s_sptr, s_sidx, f.n_long + (int)blockDim.x);
+        } else {
+            split_gene_sums(f, c, s.sr);
+        }
         __syncthreads();
         if (tr) tr[5] = global_timer_ns();
         if (tid == 0) s.sum[kT2Lik + kAqKin0] += s.sc[kScKin0LateLocal];   // fresh momenta of the late rows (refreshed last tick)
