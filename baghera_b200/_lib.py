@@ -82,6 +82,8 @@ NUTS_SLOT_Q, NUTS_SLOT_GRAD, NUTS_SLOT_VAR = 0, 1, 2
 NUTS_SLOT_FG_MEAN, NUTS_SLOT_FG_RAW, NUTS_SLOT_BG_MEAN, NUTS_SLOT_BG_RAW = 16, 17, 18, 19
 NUTS_SC_EPS, NUTS_SC_LOGP = 0, 1
 NUTS_AF_BAD_START = 21      # kAfBadStart (csrc/bgh_sampler.h): the energy at the start of a transition was not finite
+NUTS_AF_TUNE_END_US = NUTS_ASYNC_N_FL - 1     # kAfTuneEndUs: %globaltimer >> 10 (low 32 bits) at the end of the chain's last tuning transition
+NUTS_SC_RUN_START_US = NUTS_ASYNC_N_SC - 1    # kScRunStartUs: %globaltimer >> 10 at the start of the run
 
 _vp = ctypes.c_void_p
 _i32, _i64, _dbl = ctypes.c_int32, ctypes.c_int64, ctypes.c_double

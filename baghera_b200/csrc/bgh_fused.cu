@@ -828,6 +828,7 @@ __device__ __forceinline__ void tick_scalar(const AsyncParams& a, unsigned char*
                     st[6 * p.C + c] = s_sc[kScLogpProp];
                     st[7 * p.C + c] = s_sc[kScMaxDE];
                 }
+                if (draw == (long long)a.tune - 1) s_fl[kAfTuneEndUs] = (int)(unsigned)(global_timer_ns() >> 10);
                 s_fl[kAfRecSlot] = (draw >= a.tune) ? (int)(draw - a.tune) : -1;
                 if (tuning) {     // QuadPotentialDiagAdapt.update schedule
                     const int n_adapt = s_fl[kAfNAdapt];

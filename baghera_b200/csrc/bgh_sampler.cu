@@ -651,6 +651,11 @@ __global__ void nuts_async_init_kernel(const AsyncParams a, double step0, double
     sc(p, kScFgW, c) = initial_weight;
     sc(p, kScBgW, c) = 0.0;
     sc(p, kScLogSizeSub, c) = -INFINITY;
+    {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        sc(p, kScRunStartUs, c) = (double)(now >> 10);
+    }
     afl(a, kAfRecSlot, c) = -1;
     const bool real = c < p.C && (a.tune + a.draws) > 0;
     afl(a, kAfPhase, c) = real ? kPhaseRun : kPhaseFinished;

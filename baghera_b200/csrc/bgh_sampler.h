@@ -96,6 +96,10 @@ enum : int {   // extra scalars of the async machine, appended to the lock-step 
     kAscCount = BGH_NUTS_ASYNC_N_SC
 };
 static_assert(kScBgUse + 1 <= kAscCount, "async scalar numbering");
+// device timestamps (%globaltimer >> 10, i.e. units of 1.024 us): start of the run (set by the init kernel) and the end of
+// every chain's last tuning transition — seconds_tune of sampler.py is MEASURED per chain, not apportioned by leapfrogs
+constexpr int kScRunStartUs = BGH_NUTS_ASYNC_N_SC - 1;     // double: exact
+constexpr int kAfTuneEndUs = BGH_NUTS_ASYNC_N_FL - 1;      // int32: low 32 bits (differences are valid for 73 minutes)
 
 struct AsyncParams {
     NutsParams n;        // n.sc has kAscCount rows, n.partials kAsyncPartials quantities per block

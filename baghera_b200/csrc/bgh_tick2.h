@@ -41,6 +41,7 @@ static_assert(kAfFlip + 1 <= kAfCount, "tick2 flag numbering");
 
 // extra per-chain scalars of the fused kernel (rows of sc[kAscCount][Cp])
 enum : int { kScKin0LateLocal = kScBgUse + 1, kScKin0LateRep };
+static_assert(kScKin0LateRep < kScRunStartUs && kAfSubValid + 2 < kAfTuneEndUs, "the fused kernel's extra slots stay below the timestamp slots");
 static_assert(kScKin0LateRep + 1 <= kAscCount, "tick2 scalar numbering");
 
 // LL-protocol mailbox of the per-chain exchange: cell = {lo32(data), tag, hi32(data), tag}

@@ -189,11 +189,22 @@ class NutsSampler:
         st = stats.cpu().numpy()
         tree = st[:, 2, :]                                   # leapfrogs per transition and chain
         frac_tune = tree[:tune].sum() / max(tree.sum(), 1.0)
+        seconds_tune, note = total * frac_tune, "seconds_total is measured; tune / draws are apportioned by the leapfrogs of each phase"
+        if tune > 0:
+            # measured: device timestamps (units of 1.024 us) at the start of the run and at the end of every chain's last tuning
+            # transition (chains leave tuning at different ticks: the mean over chains is the time the batch spent tuning)
+            t_end = self.afl[_lib.NUTS_AF_TUNE_END_US, :C].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+            t_start = self.sc[_lib.NUTS_SC_RUN_START_US, :C].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+            dt = ((t_end - t_start) & 0xFFFFFFFF) * 1.024e-6
+            if np.all(dt > 0.0) and np.all(dt <= total * 1.05 + 1e-3):
+                seconds_tune = float(min(dt.mean(), total)) if draws > 0 else total
+                note = ("seconds_total is wall clock; seconds_tune is measured on the device (globaltimer at the end of each chain's "
+                        "last tuning transition, mean over chains), seconds_draws the rest")
         self.total_leapfrogs += int(n_ticks.value)
         self.draw += tune + draws
         out = dict(trace=trace[:draws] if keep_trace else None, stats=st, leapfrogs=tree.mean(axis=1), ticks=int(n_ticks.value),
-                   seconds_tune=total * frac_tune, seconds_draws=total * (1.0 - frac_tune), seconds_total=total, tune=tune,
-                   seconds_note="seconds_total is measured; tune / draws are apportioned by the leapfrogs of each phase")
+                   seconds_tune=seconds_tune, seconds_draws=total - seconds_tune, seconds_total=total, tune=tune,
+                   seconds_note=note)
         if stream_stats:
             out["k6"] = k6[:, :, :C]
             out["head_trace"] = head[:draws].permute(0, 2, 1)          # [draws, H, C]

@@ -171,7 +171,7 @@ def run_sampler_section(eng, args, C, seed=1, shard=None, D_total=None, dist=Non
         "us_per_tick": secs_total / max(ticks, 1) * 1e6,
         "engine": "fused persistent kernel, gene-block sharded x%d (bgh_tick2.cu)" % world if world > 1 else "bgh_nuts_run (persistent kernel)",
         "seconds_total": secs_total, "seconds_tune": out["seconds_tune"], "seconds_draws": secs,
-        "seconds_note": "seconds_total is measured (max over ranks); tune / draws are apportioned by the leapfrogs of each phase",
+        "seconds_note": "seconds_total: max over ranks; " + out.get("seconds_note", ""),
         "ess_min_scalar": min(ess.values()), "ess_per_sec": min(ess.values()) / secs, "ess": ess, "rhat": rhat,
         "ess_median_beta": float(np.median(beta_ess)), "ess_median_beta_per_sec": float(np.median(beta_ess)) / secs,
         "leapfrogs_per_draw_post_tune": float(leap[tune:].mean()), "leapfrogs_total": int(leap.sum()),
