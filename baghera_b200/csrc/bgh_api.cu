@@ -752,9 +752,10 @@ int bgh_upload(bgh_ctx* ctx, const float* chi2, const float* ld, const int32_t* 
     const bool fp = gw ? true : ctx->cfg.first_gene_partial != 0;
     const bool lp = gw ? true : ctx->cfg.last_gene_partial != 0;
     std::string err;
+    const char* ekw = getenv("BGH_PLAN_KAPPA_WARP");       // tuning only: two-level cuts for the evaluation plan as well
     int rc = build_plan(Mp, g_sorted.data(), G, ctx->n_cta, kLikWarps, fp, lp, ctx->cfg.first_gene_row,
                         ctx->cfg.last_gene_row, plan_kappa(), &ctx->plan, &err, kLikBatch, ctx->cfg.n_replicated,
-                        ctx->cfg.owns_replicated != 0);
+                        ctx->cfg.owns_replicated != 0, 0.0, (ekw && *ekw) ? atof(ekw) : -1.0);
     if (rc != BGH_OK) return fail(ctx, rc, err);
 
     {

@@ -17,12 +17,15 @@ ap.add_argument("--C", type=int, nargs="+", default=[64])
 ap.add_argument("--kappa", type=float, nargs="+", default=[6.0])
 ap.add_argument("--n", type=int, default=300)
 ap.add_argument("--model", default="gene")
+ap.add_argument("--kappa-warp", type=float, nargs="+", default=[None])
 args = ap.parse_args()
 d = synth.make_arrays(args.M, args.G)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for C in args.C:
-    for kappa in args.kappa:
+    for kappa, kw in [(k, w) for k in args.kappa for w in args.kappa_warp]:
         os.environ["BGH_PLAN_KAPPA"] = str(kappa)
+        if kw is not None:
+            os.environ["BGH_PLAN_KAPPA_WARP"] = str(kw)
         eng = Engine(d.chi2, d.ld, d.gene_id if args.model == "gene" else None, d.G, d.c, C, model=args.model)
         Q = synth.jittered_start(eng.D, C, seed=1, model=args.model)
         q = eng.to_device_layout(Q)
@@ -42,6 +45,6 @@ for C in args.C:
             a, b, n = eng.kernel_time_ms(reset=True)
             eng.set_profiling(False)
             res[mode] = (a * 1e3, b * 1e3)
-        print("C=%d kappa=%.1f split=%d  flushed: lik %.2f us fin %.2f us | steady: lik %.2f us fin %.2f us" % (
-            C, kappa, eng.n_split_genes, res["flushed"][0], res["flushed"][1], res["steady"][0], res["steady"][1]), flush=True)
+        print("C=%d kappa=%.1f kappa_warp=%s split=%d  flushed: lik %.2f us fin %.2f us | steady: lik %.2f us fin %.2f us" % (
+            C, kappa, kw, eng.n_split_genes, res["flushed"][0], res["flushed"][1], res["steady"][0], res["steady"][1]), flush=True)
         eng.close()
