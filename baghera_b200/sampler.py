@@ -150,6 +150,8 @@ class NutsSampler:
         """pm.sample(draws, tune=tune): the whole run on the device (bgh_nuts_run).  Every tick advances
         every chain by one leapfrog; chains never wait for the deepest tree of the batch.  Returns the
         same dict as :meth:`sample_lockstep` (``leapfrogs`` holds the per-draw mean tree size over chains).
+        ``progress`` is accepted for signature compatibility with :meth:`sample_lockstep` and ignored: the run is ONE blocking
+        C call whose host loop only polls the number of finished chains every ``poll_ticks`` ticks.
 
         stream_stats: the kernel also accumulates, per coordinate and chain, {sum, sum of squares, count(value - mi > 0)} of
         the recorded per-gene effects in fp64 (``k6`` [3, D, C]) and keeps the shared parameters of every draw in fp64
