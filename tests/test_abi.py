@@ -61,3 +61,27 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
                 assert "liboracle" not in txt, f
+
+
+def test_hot_loop_operand_reads_of_the_built_kernels(built_lib):
+    """Regression guard for the likelihood inner loop: on B200 a DFMA that READS three fresh source operands takes
+    3 FP64-pipe cycles instead of 2, so the operand order of `accumulate` in bgh_lik_device.cuh (and whatever ptxas makes of it)
+    sets the issue ceiling of the kernel.  Static SASS analysis of the built library (tools/sass_dfma_reads.py, the figure
+    bench.py prints as fp64_roofline.rf_ceiling): the C = 64 kernels must keep at most 48 three-operand DFMAs of the 80 of a
+    batch (round-2 start: 52 -> ceiling 75.5 %; now 37-47 -> 77-81 %)."""
+    import os
+    import shutil
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    from sass_dfma_reads import kernel_ceiling
+    so = os.path.join(root, "baghera_b200", "libbaghera_b200.so")
+    for mangled in ("_ZN3bgh22logp_grad_fused_kernelILi32ELi2ELb0EEEvNS_11FusedParamsE",
+                    "_ZN3bgh23logp_grad_chainx_kernelILi32ELi2ELb0EEEvNS_11Eval2ParamsE",
+                    "_ZN3bgh17nuts_tick2_kernelILi32ELi2ELb0EEEvNS_11Tick2ParamsE",
+                    "_ZN3bgh16nuts_tick_kernelILi32ELi2ELb0EEEvNS_10TickParamsE"):
+        r = kernel_ceiling(so, mangled)
+        assert r is not None, mangled
+        assert r["dfma_in_hot_loop"] == 80 and r["three_operand_reads"] <= 48 and r["frac_of_dfma_peak"] >= 0.76, (mangled, r)
