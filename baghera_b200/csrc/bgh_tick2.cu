@@ -340,8 +340,6 @@ __device__ __forceinline__ void tick2_pre(const Tick2Params& t, const T2Own& own
 // POST: second half of the leapfrog with the gradient the likelihood pass just wrote, per-chain sums of the
 // CTA's rows -> part[cta][quantity][chain].  Accumulators live in the (idle) likelihood staging area,
 // thread-interleaved [quantity][thread], which is also the layout the CTA reduction reads.
-// LEVEL_MAJOR (few chains per CTA row: the pass is latency-bound) walks the checked tree levels outermost.
-template <bool LEVEL_MAJOR>
 __device__ __forceinline__ void tick2_post(const Tick2Params& t, const T2Own& own, const int* s_bits, const double* s_h, const double* s_kin0c,
                                            unsigned need, unsigned char* smem_raw)
 {
@@ -377,14 +375,6 @@ __device__ __forceinline__ void tick2_post(const Tick2Params& t, const T2Own& ow
                 tot[u] = ldk(p.state + (size_t)kSlotT * vec + i[u], pol);
                 ck0[u] = nl > 0 ? *t2_ckpt(p, lm, i[u]) : make_double2(0.0, 0.0);
                 for (int l = 1; l < nl; ++l) prefetch_l1(t2_ckpt(p, lm + l, i[u]));     // deeper levels: in flight with the row's other data
-            }
-            if constexpr (!LEVEL_MAJOR) {
-#pragma unroll
-                for (int u = 0; u < kUPost; ++u) {
-                    if (r + u >= r1) break;
-                    row_finish(p, bits, h, i[u], wo, gn[u], ph[u], var[u], tot[u], ck0[u], kin, acc, kLikThreads, pol);
-                }
-                continue;
             }
             // row_finish for the kUPost rows, levels outermost: the checkpoint loads of one level are in flight for all
             // rows at once (a warp holds 32 chains at different tree positions, so it walks max(nl) levels; one row at
@@ -1629,7 +1619,7 @@ __global__ void __launch_bounds__(kLikThreads, 1) nuts_tick2_kernel(const __grid
         fence_proxy_async();   // the staging area was written through the generic proxy (scalar phase, accumulators)
         for (int cb = 0; cb < t.chain_blocks; ++cb) lik_phase<CL, CPL, GAMMA>(t.lik, smem_raw, blockIdx.x, cb, par);
         if (tr) tr[9] = global_timer_ns();
-        tick2_post<true>(t, own, s_bits, s_h, s_kin0c, s_need, smem_raw);
+        tick2_post(t, own, s_bits, s_h, s_kin0c, s_need, smem_raw);
         if (tr) tr[1] = global_timer_ns();
         grid_barrier(t.bar, target, t.status);
         if (tr) tr[2] = global_timer_ns();
