@@ -119,6 +119,7 @@ struct Chunk {
     std::vector<std::vector<std::string>> local_labels;
     int64_t rows = 0;
     std::string err;
+    const char* err_at = nullptr;      // start of the offending line (for the file line number of the message)
 };
 
 }  // namespace
@@ -211,8 +212,8 @@ int bgh_csv_read(const char* path, int32_t sep_char, int32_t n_threads, bgh_tabl
             if (le == p) { p = next; continue; }   // blank line (pandas skips them)
             const int n = split_line(p, le, sep, f.data(), ncol);
             if (n != ncol) {
-                ch.err = "row " + std::to_string(ch.rows + 1) + " of thread range " + std::to_string(t) + " has " +
-                         std::to_string(n) + " fields, the header has " + std::to_string(ncol);
+                ch.err = "has " + std::to_string(n) + " fields, the header has " + std::to_string(ncol);
+                ch.err_at = p;
                 return;
             }
             for (int c = 0; c < ncol; ++c) {
@@ -221,6 +222,7 @@ int bgh_csv_read(const char* path, int32_t sep_char, int32_t n_threads, bgh_tabl
                     double v;
                     if (!parse_f64(sv, &v)) {
                         ch.err = "column '" + T->names[c] + "': cannot parse '" + std::string(sv) + "' as a number";
+                        ch.err_at = p;
                         return;
                     }
                     ch.f64[c].push_back(v);
@@ -250,13 +252,22 @@ int bgh_csv_read(const char* path, int32_t sep_char, int32_t n_threads, bgh_tabl
         work(0);
         for (auto& x : th) x.join();
     }
-    munmap((void*)data, size);
     for (int t = 0; t < nt; ++t)
         if (!chunks[t].err.empty()) {
-            g_ingest_error = "bgh_csv_read: " + chunks[t].err;
+            // the FILE line of the offending row (1-based, header = line 1), whichever thread range it fell into
+            int64_t line = 1;
+            for (const char* c = data; chunks[t].err_at && c < chunks[t].err_at;) {
+                const char* q = (const char*)memchr(c, '\n', (size_t)(chunks[t].err_at - c));
+                if (!q) break;
+                ++line;
+                c = q + 1;
+            }
+            g_ingest_error = "bgh_csv_read: line " + std::to_string(line) + ": " + chunks[t].err;
+            munmap((void*)data, size);
             delete T;
             return BGH_EINVAL;
         }
+    munmap((void*)data, size);
 
     // ---- merge: global sorted dictionaries, concatenated columns -------------------------------------
     int64_t rows = 0;

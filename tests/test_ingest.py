@@ -95,3 +95,20 @@ def test_errors(tmp_path, built_lib):
     p.write_text("chr,maf,l,sample_size,z\n1,0.2,1,10,1\n")
     with pytest.raises(ingest.IngestError, match="'gene' not found"):
         ingest.model_inputs(str(p))
+
+
+def test_error_reports_the_file_line(tmp_path, built_lib):
+    """A bad row deep inside a file that several threads parse is reported with its FILE line number (header = line 1),
+    not with a row index relative to a thread's byte range."""
+    rows = ["chr,maf,l,gene,sample_size,z"] + ["1,0.2,%d.5,G%d,10,1.0" % (i % 7 + 1, i % 50) for i in range(20_000)]
+    bad_line = 15_432                                  # 1-based file line
+    rows[bad_line - 1] = "1,0.2,oops,G1,10,1.0"
+    p = tmp_path / "deep.csv"
+    p.write_text("\n".join(rows) + "\n")
+    for threads in (1, 4):
+        with pytest.raises(ingest.IngestError, match=r"line %d: column 'l': cannot parse 'oops'" % bad_line):
+            ingest.read_snp_table(str(p), n_threads=threads)
+    rows[bad_line - 1] = "1,0.2,1.5,G1,10"
+    p.write_text("\n".join(rows) + "\n")
+    with pytest.raises(ingest.IngestError, match=r"line %d: has 5 fields" % bad_line):
+        ingest.read_snp_table(str(p), n_threads=4)
